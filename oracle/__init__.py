@@ -1,0 +1,5 @@
+"""CPU oracle for the neural-tape-modeling recurrent forward pass.
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs -- never by the product package.
+"""
