@@ -1,0 +1,330 @@
+#!/usr/bin/env python3
+"""Headline benchmark: GRU-HS[64] samples/s (BASELINE.json metric), one JSON line on stdout.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mode fp32|tf32|bf16|tf32x3]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+           bench.py --gpus N --steps K --warmup W
+
+Workload (config.workload): BASELINE.json configs[1] -- the cfg-2 checkpoint (GRU-HS[64]-L[DCPreESR] AKAI),
+1024 streams x 60 s of synthetic 48 kHz audio per GPU, predict() semantics (zero state -> 1024-sample warm
+start -> the signal).  A "step" is one full pass over that batch.  Multi-GPU: streams are sharded, every rank
+runs its own 1024 streams with no data-path collective (weak scaling); value = all samples / max-over-ranks time.
+
+  value          device-resident: inputs and outputs in HBM, CUDA events around K steps on the launching stream
+  e2e            the same pass through RNN.predict_host (ntm_gru_predict_host): pinned HOST input, HOST output,
+                 host<->device copies inside the timed region
+  roofline       contract asks for the tensor-pipe fraction: achieved = samples/s x 25088 FLOP (BASELINE.md
+                 section 4) over the measured bf16 peak of MEASURED_PEAKS.json; extra keys give the honest bound of
+                 the kernel that actually ran (fp32 FMA pipe / MUFU) and the (negligible) HBM rate
+  cpu_baseline   oracle/ref_torch.py (the reference's own torch.nn.GRU arithmetic) on the host cores, bounded sample
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+FS = 48000
+FLOP_PER_SAMPLE = 25088          # 2*(192*64 + 192 + 64), BASELINE.md section 4
+BYTES_PER_SAMPLE = 8             # x in + y out
+WORKLOAD = "cfg2: GRU-HS[64]-L[DCPreESR] AKAI _BEST, {B} streams x {sec:g} s synthetic 48 kHz audio per GPU"
+
+
+def load_sd(tag):
+    z = np.load(os.path.join(ROOT, "tests", "golden", f"ckpt_{tag}.npz"))
+    return {k: torch.from_numpy(z[k]) for k in z.files if k not in ("model_type", "weights_dir")}
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["bf16_tflops_sustained"]), float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json, sustained)"
+    except Exception:
+        return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def __enter__(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        try:
+            rows = [r.split(",") for r in open(self.path).read().strip().splitlines() if r.strip()]
+            sm = sorted(float(r[0]) for r in rows)
+            out["sm_mhz"] = sm[len(sm) // 2]
+            out["sm_max_mhz"] = float(rows[0][1])
+            out["power_w_max"] = max(float(r[2]) for r in rows)
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            out["reasons"] = [n for i, n in enumerate(names) if any("Active" == r[3 + i].strip() for r in rows)]
+            out["samples"] = len(rows)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        return out
+
+
+def cpu_baseline(B, seg_count, threads):
+    """The reference's arithmetic (torch.nn.GRU + Linear on CPU, oracle/ref_torch.py) on a bounded sample:
+    forward over `seg_count` 2048-sample segments of B streams with the broadcast warm state."""
+    from oracle import ref_torch
+    from ntm_b200 import signals
+    torch.set_num_threads(threads)
+    net = ref_torch.RefNet(load_sd("cfg2"))
+    T = 2048 * seg_count
+    x = torch.from_numpy(signals.stream_batch(B, T, dur=60.0)).reshape(B, 1, T)
+    net.predict(x[:, :, :2048])                                  # warm-up of the MKL/oneDNN paths
+    t0 = time.perf_counter()
+    net.predict(x)
+    dt = time.perf_counter() - t0
+    return B * T / dt, f"{B} streams x {T} samples ({seg_count} x 2048-sample segments), torch {torch.__version__}"
+
+
+def run_reference(args, rank):
+    """`--impl reference`: the reference's CPU path (its torch.nn.GRU arithmetic via oracle/ref_torch.py) with all
+    host threads, on a bounded sample of the same workload; rank 0 only."""
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    from oracle import ref_torch
+    from ntm_b200 import signals
+    torch.set_num_threads(threads)
+    net = ref_torch.RefNet(load_sd("cfg2"))
+    B, T = args.streams, 4096
+    x = torch.from_numpy(signals.stream_batch(B, T, dur=60.0)).reshape(B, 1, T)
+    for _ in range(args.warmup):
+        net.predict(x)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        net.predict(x)
+    dt = time.perf_counter() - t0
+    value = B * T * args.steps / dt
+    sample = f"{B} streams x {T} samples per step (bounded sample of the 60 s workload)"
+    print(json.dumps({
+        "impl": "reference", "metric": "GRU-HS64 samples/sec", "value": value, "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD.format(B=args.streams, sec=args.seconds), "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "realtime_streams": value / FS,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="fp32", choices=["fp32", "tf32", "bf16", "tf32x3"])
+    ap.add_argument("--streams", type=int, default=1024)
+    ap.add_argument("--seconds", type=float, default=60.0)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-aux", action="store_true", help="skip the batch-1 / large-batch side measurements")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import ntm_b200
+    from ntm_b200 import lib, signals
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: ntm_b200 has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    B, T = args.streams, int(round(args.seconds * FS))
+    model = ntm_b200.RNN(input_size=1, hidden_size=64, output_size=1, skip=False).to(dev)
+    model.load_state_dict(load_sd("cfg2"))
+    model.mode = args.mode
+    x = signals.stream_batch_device(B, T, dev, first_stream=rank * B, dur=args.seconds).reshape(B, 1, T)
+    torch.cuda.synchronize(dev)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    L = lib.load()
+    with torch.inference_mode():
+        # ---- device-resident pass -------------------------------------------------------------------
+        for _ in range(args.warmup):
+            y = model.predict(x)
+        del y
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 2)]
+        barrier()
+        launches0 = L.ntm_query(lib.Q_KERNEL_LAUNCHES)
+        with ClockSampler(local_rank) as clk:
+            ev[0].record()
+            for i in range(args.steps):
+                model.initialize_hidden()
+                model.warm_start()
+                model.hidden = model.hidden.expand(1, B, 64).contiguous()
+                ev[2 + 2 * i].record()
+                y = model(x)                       # the persistent kernel: all T steps of all B streams
+                ev[3 + 2 * i].record()
+            ev[1].record()
+            barrier()
+        launches = L.ntm_query(lib.Q_KERNEL_LAUNCHES) - launches0
+        total_ms = ev[0].elapsed_time(ev[1])
+        kern_ms = sum(ev[2 + 2 * i].elapsed_time(ev[3 + 2 * i]) for i in range(args.steps)) / args.steps
+        checksum = float(y[:, :, ::4801].double().sum())
+        del y
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+        value = world * B * T * args.steps / (total_ms * 1e-3)
+
+        # ---- end to end: pinned host in -> engine pipeline -> pinned host out -------------------------
+        import psutil
+        avail = psutil.virtual_memory().available
+        need = 2 * B * T * 4 * max(1, min(world, 8))
+        T_e = T if need < 0.5 * avail else max(FS, int(0.25 * avail / (8 * B * max(1, world))) // FS * FS)
+        xh = torch.empty((B, 1, T_e), dtype=torch.float32, pin_memory=True)
+        xh.copy_(x[:, :, :T_e])
+        model.predict_host(xh)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            yh = model.predict_host(xh)
+        torch.cuda.synchronize(dev)
+        e2e_s = time.perf_counter() - t0
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_value = world * B * T_e * args.e2e_steps / float(t.item())
+        e2e_ok = bool(torch.isfinite(yh[:, :, ::4801]).all())
+        del xh, yh
+
+        # ---- side measurements (rank 0, outside the timed regions) -------------------------------------
+        aux = {}
+        if rank == 0 and not args.no_aux:
+            aux = aux_measurements(ntm_b200, signals, dev, args.mode)
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    clocks = clk.summary()
+    tensor_peak, hbm_peak, peak_src = measured_peaks()
+    sps_kernel = B * T / (kern_ms * 1e-3)
+    achieved_tflops = sps_kernel * FLOP_PER_SAMPLE / 1e12
+    f_clk = (clocks.get("sm_mhz") or 1965.0) * 1e6
+    sm_count = L.ntm_query(lib.Q_SM_COUNT)
+    line = {
+        "metric": "GRU-HS64 samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32", "bf16": "bf16", "tf32x3": "tf32x3"}[args.mode],
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD.format(B=B, sec=args.seconds), "streams_per_gpu": B, "samples_per_stream": T,
+                   "sample_rate": FS, "mode": args.mode, "parallelism": f"stream-sharded x{world}, no collective",
+                   "l2": "inputs (%.1f GB per GPU) are larger than L2; no flush needed" % (B * T * 4 / 1e9)},
+        "realtime_streams": value / FS,
+        "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": B * T_e * 4,
+                "d2h_bytes_per_step": B * T_e * 4, "samples_per_stream": T_e, "finite": e2e_ok,
+                "api": "RNN.predict_host -> ntm_gru_predict_host (pinned host buffers)"},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {
+            "bound": "tensor", "achieved": achieved_tflops, "peak": tensor_peak, "unit": "TFLOP/s",
+            "frac": achieved_tflops / tensor_peak, "traffic": None, "peak_source": peak_src,
+            "kernel_ms": kern_ms, "kernel": "gru_fp32_kernel" if args.mode == "fp32" else f"gru_{args.mode}",
+            "fp32_fma_peak_tflops": sm_count * 128 * 2 * f_clk / 1e12,
+            "frac_of_fp32_fma_peak": achieved_tflops / (sm_count * 128 * 2 * f_clk / 1e12),
+            "mufu_bound_samples_per_s": sm_count * 16 * f_clk / 192,
+            "hbm_gbs_achieved": sps_kernel * BYTES_PER_SAMPLE / 1e9, "hbm_frac": sps_kernel * BYTES_PER_SAMPLE / 1e9 / hbm_peak,
+        },
+        "checksum": checksum,
+        "aux": aux,
+    }
+    if not args.no_cpu:
+        threads = os.cpu_count() or 1
+        v, sample = cpu_baseline(min(B, 1024), 4, threads)
+        line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def aux_measurements(ntm_b200, signals, dev, mode):
+    """cfg 5 (batch-1 real-time blocks) and a large-batch point, each a few hundred ms."""
+    out = {}
+    m1 = ntm_b200.RNN(1, 64, 1, False).to(dev)
+    m1.load_state_dict(load_sd("cfg1"))
+    x1 = torch.from_numpy(signals.signal("sweepnoise", 480000, seed=0)).to(dev).reshape(1, 1, -1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    m1.predict(x1)
+    m1.initialize_hidden(); m1.warm_start()
+    e0.record(); m1(x1); e1.record(); torch.cuda.synchronize(dev)
+    out["batch1_kernel_ns_per_sample"] = e0.elapsed_time(e1) * 1e6 / 480000
+    nblk = 2000
+    m1.initialize_hidden(); m1.warm_start()
+    for k in range(50):
+        m1(x1[:, :, 64 * k:64 * k + 64])
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for k in range(nblk):
+        m1(x1[:, :, 64 * k:64 * k + 64])
+    torch.cuda.synchronize(dev)
+    out["batch1_block64_ns_per_sample_incl_launch"] = (time.perf_counter() - t0) * 1e9 / (nblk * 64)
+    mb = ntm_b200.RNN(1, 64, 1, False).to(dev)
+    mb.load_state_dict(load_sd("cfg2"))
+    mb.mode = mode
+    Bb, Tb = 16384, 24000
+    xb = signals.stream_batch_device(Bb, Tb, dev, dur=10.0).reshape(Bb, 1, Tb)
+    mb.predict(xb[:, :, :2400])
+    mb.initialize_hidden(); mb.warm_start(); mb.hidden = mb.hidden.expand(1, Bb, 64).contiguous()
+    e0.record(); mb(xb); e1.record(); torch.cuda.synchronize(dev)
+    out["large_batch"] = {"streams": Bb, "samples_per_stream": Tb, "samples_per_s": Bb * Tb / (e0.elapsed_time(e1) * 1e-3)}
+    return out
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,129 @@
+/*
+ * ntm_b200.h -- C ABI of the B200-native engine for the recurrent forward pass of
+ * 01tot10/neural-tape-modeling (GRU-HS[64] + Linear head, optional time-varying delay line).
+ *
+ * The reference has no FFI of its own for this path: its boundary is the Python torch.nn.Module API in
+ * code/model.py.  Each entry point below names the reference method whose arithmetic it replaces; the
+ * Python classes in neural-tape-modeling_b200/model.py (same names/signatures as code/model.py) call
+ * exactly these symbols through ctypes (see INTEGRATION.md for the binding a reference maintainer adds).
+ *
+ * Conventions
+ *   - Plain pointers and sizes only.  Unless a name ends in _host, data pointers are DEVICE pointers on the
+ *     handle's device and `stream` is a cudaStream_t (NULL = legacy default stream).  Launches are
+ *     asynchronous; nothing here synchronises unless stated.
+ *   - Audio tensors are the reference's (B, 1, T) float32 layout: row b starts at ptr + b*ld, ld >= T.
+ *   - Return value: 0 (NTM_OK) or a negative NTM_E* code; never throws, never aborts.  After NTM_ECUDA,
+ *     ntm_last_cuda_error() returns the cudaError_t of the calling thread's last failure.
+ *   - Caller owns every buffer passed in; the engine owns only the handle (prepare/destroy) and the
+ *     staging buffers of the *_host entry points (allocated on first use, freed by ntm_destroy).
+ */
+#ifndef NTM_B200_H
+#define NTM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden */
+#endif
+
+#define NTM_API_VERSION 1
+
+/* error codes */
+#define NTM_OK            0
+#define NTM_EINVAL       (-1)   /* bad argument (null pointer, negative size, ld < T, ...) */
+#define NTM_EUNSUPPORTED (-2)   /* hidden size / mode not built into this library */
+#define NTM_ENOMEM       (-3)
+#define NTM_ECUDA        (-4)   /* a CUDA runtime call failed: see ntm_last_cuda_error() */
+#define NTM_EDELAY       (-5)   /* a delay value exceeds the history length D (the reference's assert,
+                                   code/model.py:283) -- only returned by ntm_delay_check */
+#define NTM_ENODEVICE    (-6)   /* no CUDA device / not an sm_100 device */
+
+/* arithmetic modes of the hidden-to-hidden contraction (gates, state and head are always fp32) */
+#define NTM_MODE_FP32     0     /* fp32 FFMA on CUDA cores, libm-grade activations: the parity anchor */
+#define NTM_MODE_TF32     1     /* tensor cores, tf32 operands, fp32 accumulate */
+#define NTM_MODE_BF16     2     /* tensor cores, bf16 operands, fp32 accumulate (opt-in, lower accuracy) */
+#define NTM_MODE_TF32X3   3     /* tensor cores, 3xTF32 split (fp32-grade result) */
+
+/* ntm_query selectors */
+#define NTM_Q_VERSION        0
+#define NTM_Q_DEVICE_COUNT   1
+#define NTM_Q_SM_COUNT       2   /* of the current device */
+#define NTM_Q_MODE_MASK      3   /* bit m set <=> mode m is implemented */
+#define NTM_Q_KERNEL_LAUNCHES 4  /* number of engine kernels launched by this process so far */
+
+int         ntm_query(int what);
+const char* ntm_strerror(int code);
+int         ntm_last_cuda_error(void);
+
+/*
+ * Pack one model's parameters (HOST pointers, PyTorch layouts, gate row order r,z,n) into an engine-owned
+ * device blob on `device`.   Replaces: RNN.__init__/load_state_dict parameter ownership, code/model.py:44-45
+ * (b_out != NULL) and DiffDelRNN, code/model.py:364-365 (b_out == NULL).
+ *   w_ih (3H,1)  w_hh (3H,H)  b_ih (3H)  b_hh (3H)  w_out (1,H)  b_out (1) or NULL.   H must be 64.
+ */
+int  ntm_gru_prepare(const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                     const float* w_out, const float* b_out, int H, int device, void** handle);
+void ntm_destroy(void* handle);
+
+/*
+ * y = head(GRU(x, h_in)); h_out receives the final state.
+ * Replaces: RNN.forward, code/model.py:67-88  (`self.GRU(x, self.hidden)` + `self.output(x)` [+ skip]).
+ *   x (B rows, ld ldx)  y (B rows, ld ldy)  h_in (B x 64 contiguous, NULL = zero state, the reference's
+ *   `hidden = None`, code/model.py:50-52)  h_out (B x 64; may alias h_in).  T == 0 copies h_in to h_out.
+ */
+int ntm_gru_forward(void* handle, int mode, const float* x, int64_t ldx, float* y, int64_t ldy,
+                    const float* h_in, float* h_out, int64_t B, int64_t T, int skip, void* stream);
+
+/*
+ * pre_d = head(GRU(x, h));  y = delay(pre_d, d)  in ONE kernel (delay read fused after the GRU output).
+ * Replaces: DiffDelRNN.forward, code/model.py:393-424 (GRU + Linear(bias=False) + self.diffdel).
+ *   d: delay in samples per output sample.  hist_in / hist_out: (B x D) carried delay history
+ *   (TimeVaryingDelayLine.buffer, code/model.py:267,314-315); hist_out must not alias hist_in.
+ *   warmup != 0: y = pre_d, history still rolled (code/model.py:288-292).
+ */
+int ntm_diffdel_forward(void* handle, int mode, const float* x, int64_t ldx, const float* d, int64_t ldd,
+                        float* y, int64_t ldy, float* pre_d, int64_t ldp, const float* h_in, float* h_out,
+                        const float* hist_in, float* hist_out,
+                        int64_t B, int64_t T, int64_t D, int warmup, int skip, void* stream);
+
+/*
+ * Stand-alone time-varying fractional delay line.
+ * Replaces: TimeVaryingDelayLine.forward, code/model.py:269-320 (used alone by apply_delay,
+ * code/test-model.py:259-290).  Same argument meaning as above; x may not alias y.
+ */
+int ntm_delay_forward(const float* x, int64_t ldx, const float* d, int64_t ldd, float* y, int64_t ldy,
+                      const float* hist_in, float* hist_out, int64_t B, int64_t T, int64_t D,
+                      int warmup, int device, void* stream);
+
+/* The reference's `assert self.max_delay >= torch.max(dt)` (code/model.py:283).  SYNCHRONISES the stream.
+ * Returns NTM_EDELAY if any d[b][t] > D. */
+int ntm_delay_check(const float* d, int64_t ldd, int64_t B, int64_t T, int64_t D, int device, void* stream);
+
+/*
+ * Whole-signal prediction from HOST buffers (page-locked for full speed): time-chunked H2D copy, kernel and
+ * D2H copy pipelined on the engine's own streams.  Replaces the loop of RNN.predict, code/model.py:218-246
+ * (host->device at code/test-model.py:427-433, device->host at :525).  SYNCHRONOUS.
+ *   x_host, y_host: B x T contiguous.  h_host: B x 64 in-out (initial state in, final state out).
+ *   chunk_T: samples per pipelined chunk (0 = engine default).
+ */
+int ntm_gru_predict_host(void* handle, int mode, const float* x_host, float* y_host, float* h_host,
+                         int64_t B, int64_t T, int skip, int64_t chunk_T);
+
+/* DiffDelRNN.predict (code/model.py:618-653) from HOST buffers; hist_host: B x D in-out. */
+int ntm_diffdel_predict_host(void* handle, int mode, const float* x_host, const float* d_host,
+                             float* y_host, float* pre_d_host, float* h_host, float* hist_host,
+                             int64_t B, int64_t T, int64_t D, int skip, int64_t chunk_T);
+
+/* Tuning knob for experiments: streams per CTA / k-split of the fp32 kernel (0 = automatic). */
+int ntm_set_tuning(int streams_per_cta, int ksplit);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* NTM_B200_H */

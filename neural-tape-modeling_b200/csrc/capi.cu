@@ -1,0 +1,399 @@
+// extern "C" launch layer: the drop-in boundary declared in include/ntm_b200.h.
+// No torch types, no exceptions, no hidden allocation on the device-pointer entry points.
+#include <new>
+#include <string.h>
+
+#include "../../include/ntm_b200.h"
+#include "ntm_common.cuh"
+
+namespace ntm {
+unsigned long long g_launches = 0;
+}
+
+namespace {
+
+constexpr unsigned HANDLE_MAGIC = 0x4e544d42u;   // "NTMB"
+thread_local int t_last_cuda = 0;
+int g_tune_s = 0, g_tune_ks = 0;
+
+struct HostPipe {            // staging of the *_host entry points
+    cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[2] = {}, ev_run[2] = {}, ev_out[2] = {};
+    float* buf = nullptr;    // one slab: x[2], d[2], y[2], pre[2], h, hist[2]
+    size_t cap = 0;
+    bool ready = false;
+};
+
+struct Handle {
+    unsigned magic;
+    int device;
+    int sm_count;
+    int has_bias;
+    float* blob;
+    HostPipe pipe;
+};
+
+int cuda_fail(cudaError_t e)
+{
+    t_last_cuda = (int)e;
+    return NTM_ECUDA;
+}
+#define CU(call)                                   \
+    do {                                           \
+        cudaError_t e_ = (call);                   \
+        if (e_ != cudaSuccess) return cuda_fail(e_); \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+Handle* as_handle(void* p)
+{
+    Handle* h = static_cast<Handle*>(p);
+    return (h && h->magic == HANDLE_MAGIC) ? h : nullptr;
+}
+
+bool mode_supported(int mode) { return mode == NTM_MODE_FP32; }
+
+int run_gru(Handle* hd, int mode, const ntm::GruArgs& a, cudaStream_t st)
+{
+    if (!mode_supported(mode)) return NTM_EUNSUPPORTED;
+    CU(ntm::launch_gru_fp32(a, hd->sm_count, g_tune_s, g_tune_ks, st));
+    return NTM_OK;
+}
+
+int pipe_init(Handle* hd, size_t floats)
+{
+    HostPipe& p = hd->pipe;
+    if (!p.ready) {
+        CU(cudaStreamCreateWithFlags(&p.s_in, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&p.s_run, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&p.s_out, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CU(cudaEventCreateWithFlags(&p.ev_in[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&p.ev_run[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&p.ev_out[i], cudaEventDisableTiming));
+        }
+        p.ready = true;
+    }
+    if (p.cap < floats) {
+        if (p.buf) CU(cudaFree(p.buf));
+        p.buf = nullptr;
+        p.cap = 0;
+        cudaError_t e = cudaMalloc(&p.buf, floats * sizeof(float));
+        if (e == cudaErrorMemoryAllocation) { cudaGetLastError(); return NTM_ENOMEM; }
+        CU(e);
+        p.cap = floats;
+    }
+    return NTM_OK;
+}
+
+// Shared body of the two *_host entry points (d_host == nullptr: plain GRU).
+int predict_host(Handle* hd, int mode, const float* x_host, const float* d_host, float* y_host, float* pre_host,
+                 float* h_host, float* hist_host, int64_t B, int64_t T, int64_t D, int skip, int64_t chunk_T)
+{
+    if (!x_host || !y_host || !h_host || B < 0 || T < 0) return NTM_EINVAL;
+    const bool delay = d_host != nullptr;
+    if (delay && (!pre_host || !hist_host || D < 0)) return NTM_EINVAL;
+    if (!mode_supported(mode)) return NTM_EUNSUPPORTED;
+    if (B == 0) return NTM_OK;
+    DeviceGuard g(hd->device);
+    if (!g.ok) return cuda_fail(cudaErrorInvalidDevice);
+
+    int64_t C = chunk_T > 0 ? chunk_T : (int64_t)((64ll << 20) / (4 * B));   // ~64 MiB per staged array
+    if (C < 2048) C = 2048;
+    C = (C + 63) & ~63ll;                                                     // keep rows 256-byte aligned
+    if (C > T) C = (T + 63) & ~63ll;
+    if (C == 0) C = 64;
+    const size_t slab = (size_t)B * (size_t)C;
+    const size_t narr = delay ? 8 : 4;
+    const size_t hfl = (size_t)B * 64, histfl = delay ? (size_t)B * (size_t)D : 0;
+    int rc = pipe_init(hd, narr * slab + hfl + 2 * histfl + 64);
+    if (rc != NTM_OK) return rc;
+    HostPipe& p = hd->pipe;
+    float* dx[2] = {p.buf, p.buf + slab};
+    float* dy[2] = {p.buf + 2 * slab, p.buf + 3 * slab};
+    float* dd[2] = {nullptr, nullptr};
+    float* dp[2] = {nullptr, nullptr};
+    if (delay) {
+        dd[0] = p.buf + 4 * slab; dd[1] = p.buf + 5 * slab;
+        dp[0] = p.buf + 6 * slab; dp[1] = p.buf + 7 * slab;
+    }
+    float* dh = p.buf + narr * slab;
+    float* dhist[2] = {dh + hfl, dh + hfl + histfl};
+
+    CU(cudaMemcpyAsync(dh, h_host, hfl * sizeof(float), cudaMemcpyHostToDevice, p.s_run));
+    if (delay && histfl)
+        CU(cudaMemcpyAsync(dhist[0], hist_host, histfl * sizeof(float), cudaMemcpyHostToDevice, p.s_run));
+
+    const int64_t nchunks = (T + C - 1) / C;
+    int hcur = 0;
+    for (int64_t c = 0; c < nchunks; ++c) {
+        const int64_t t0 = c * C, n = (T - t0) < C ? (T - t0) : C;
+        const int k = (int)(c & 1);
+        // host -> device (stream s_in); the staging slot is free once the kernel of chunk c-2 finished
+        if (c >= 2) CU(cudaStreamWaitEvent(p.s_in, p.ev_run[k], 0));
+        CU(cudaMemcpy2DAsync(dx[k], C * sizeof(float), x_host + t0, T * sizeof(float), n * sizeof(float), B,
+                             cudaMemcpyHostToDevice, p.s_in));
+        if (delay)
+            CU(cudaMemcpy2DAsync(dd[k], C * sizeof(float), d_host + t0, T * sizeof(float), n * sizeof(float), B,
+                                 cudaMemcpyHostToDevice, p.s_in));
+        CU(cudaEventRecord(p.ev_in[k], p.s_in));
+        // recurrent kernel (stream s_run); its output slot is free once chunk c-2 was copied out
+        CU(cudaStreamWaitEvent(p.s_run, p.ev_in[k], 0));
+        if (c >= 2) CU(cudaStreamWaitEvent(p.s_run, p.ev_out[k], 0));
+        ntm::GruArgs a{};
+        a.blob = hd->blob; a.x = dx[k]; a.y = dy[k]; a.h_in = dh; a.h_out = dh;
+        a.B = B; a.T = n; a.ldx = C; a.ldy = C; a.skip = skip;
+        if (delay) {
+            a.d = dd[k]; a.ldd = C; a.pre = dp[k]; a.ldp = C; a.D = (int)D;
+            a.hist_in = dhist[hcur]; a.hist_out = dhist[hcur ^ 1];
+            hcur ^= 1;
+        }
+        rc = run_gru(hd, mode, a, p.s_run);
+        if (rc != NTM_OK) return rc;
+        CU(cudaEventRecord(p.ev_run[k], p.s_run));
+        // device -> host (stream s_out)
+        CU(cudaStreamWaitEvent(p.s_out, p.ev_run[k], 0));
+        CU(cudaMemcpy2DAsync(y_host + t0, T * sizeof(float), dy[k], C * sizeof(float), n * sizeof(float), B,
+                             cudaMemcpyDeviceToHost, p.s_out));
+        if (delay)
+            CU(cudaMemcpy2DAsync(pre_host + t0, T * sizeof(float), dp[k], C * sizeof(float), n * sizeof(float), B,
+                                 cudaMemcpyDeviceToHost, p.s_out));
+        CU(cudaEventRecord(p.ev_out[k], p.s_out));
+    }
+    CU(cudaMemcpyAsync(h_host, dh, hfl * sizeof(float), cudaMemcpyDeviceToHost, p.s_run));
+    if (delay && histfl)
+        CU(cudaMemcpyAsync(hist_host, dhist[hcur], histfl * sizeof(float), cudaMemcpyDeviceToHost, p.s_run));
+    CU(cudaStreamSynchronize(p.s_in));
+    CU(cudaStreamSynchronize(p.s_run));
+    CU(cudaStreamSynchronize(p.s_out));
+    return NTM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ntm_query(int what)
+{
+    switch (what) {
+        case NTM_Q_VERSION: return NTM_API_VERSION;
+        case NTM_Q_DEVICE_COUNT: {
+            int n = 0;
+            if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+            return n;
+        }
+        case NTM_Q_SM_COUNT: {
+            int dev = 0, n = 0;
+            if (cudaGetDevice(&dev) != cudaSuccess ||
+                cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+                cudaGetLastError();
+                return 0;
+            }
+            return n;
+        }
+        case NTM_Q_MODE_MASK: return 1 << NTM_MODE_FP32;
+        case NTM_Q_KERNEL_LAUNCHES: return (int)(ntm::g_launches & 0x7fffffffull);
+        default: return NTM_EINVAL;
+    }
+}
+
+const char* ntm_strerror(int code)
+{
+    switch (code) {
+        case NTM_OK: return "ok";
+        case NTM_EINVAL: return "invalid argument";
+        case NTM_EUNSUPPORTED: return "unsupported hidden size or arithmetic mode";
+        case NTM_ENOMEM: return "out of device memory";
+        case NTM_ECUDA: return cudaGetErrorString((cudaError_t)t_last_cuda);
+        case NTM_EDELAY: return "delay exceeds max_delay (history length)";
+        case NTM_ENODEVICE: return "no usable CUDA device (sm_100 required)";
+        default: return "unknown error";
+    }
+}
+
+int ntm_last_cuda_error(void) { return t_last_cuda; }
+
+int ntm_set_tuning(int streams_per_cta, int ksplit)
+{
+    if (streams_per_cta < 0 || ksplit < 0) return NTM_EINVAL;
+    g_tune_s = streams_per_cta;
+    g_tune_ks = ksplit;
+    return NTM_OK;
+}
+
+int ntm_gru_prepare(const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, const float* w_out,
+                    const float* b_out, int H, int device, void** handle)
+{
+    if (!handle) return NTM_EINVAL;
+    *handle = nullptr;
+    if (!w_ih || !w_hh || !b_ih || !b_hh || !w_out) return NTM_EINVAL;
+    if (H != ntm::H64) return NTM_EUNSUPPORTED;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return NTM_ENODEVICE; }
+    if (device < 0 || device >= ndev) return NTM_EINVAL;
+    int major = 0;
+    CU(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    if (major != 10) return NTM_ENODEVICE;          // the library carries sm_100a code only
+    DeviceGuard g(device);
+    if (!g.ok) return cuda_fail(cudaErrorInvalidDevice);
+
+    using L = ntm::BlobLayout;
+    float* host = new (std::nothrow) float[L::FP32_END];
+    if (!host) return NTM_ENOMEM;
+    memset(host, 0, sizeof(float) * L::FP32_END);
+    memcpy(host + L::W_HH, w_hh, sizeof(float) * ntm::G192 * ntm::H64);
+    memcpy(host + L::W_IH, w_ih, sizeof(float) * ntm::G192);
+    memcpy(host + L::B_IH, b_ih, sizeof(float) * ntm::G192);
+    memcpy(host + L::B_HH, b_hh, sizeof(float) * ntm::G192);
+    memcpy(host + L::W_OUT, w_out, sizeof(float) * ntm::H64);
+    host[L::B_OUT] = b_out ? b_out[0] : 0.0f;
+
+    Handle* hd = new (std::nothrow) Handle();
+    if (!hd) { delete[] host; return NTM_ENOMEM; }
+    hd->magic = HANDLE_MAGIC;
+    hd->device = device;
+    hd->has_bias = b_out != nullptr;
+    hd->blob = nullptr;
+    cudaError_t e = cudaDeviceGetAttribute(&hd->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (e == cudaSuccess) e = cudaMalloc(&hd->blob, sizeof(float) * L::FP32_END);
+    if (e == cudaSuccess) e = cudaMemcpy(hd->blob, host, sizeof(float) * L::FP32_END, cudaMemcpyHostToDevice);
+    delete[] host;
+    if (e != cudaSuccess) {
+        if (hd->blob) cudaFree(hd->blob);
+        delete hd;
+        return cuda_fail(e);
+    }
+    *handle = hd;
+    return NTM_OK;
+}
+
+void ntm_destroy(void* handle)
+{
+    Handle* hd = as_handle(handle);
+    if (!hd) return;
+    DeviceGuard g(hd->device);
+    HostPipe& p = hd->pipe;
+    if (p.ready) {
+        cudaStreamDestroy(p.s_in); cudaStreamDestroy(p.s_run); cudaStreamDestroy(p.s_out);
+        for (int i = 0; i < 2; ++i) {
+            cudaEventDestroy(p.ev_in[i]); cudaEventDestroy(p.ev_run[i]); cudaEventDestroy(p.ev_out[i]);
+        }
+    }
+    if (p.buf) cudaFree(p.buf);
+    if (hd->blob) cudaFree(hd->blob);
+    hd->magic = 0;
+    delete hd;
+}
+
+static int copy_state(const float* h_in, float* h_out, int64_t B, cudaStream_t st)
+{
+    if (h_in == h_out) return NTM_OK;
+    if (h_in) CU(cudaMemcpyAsync(h_out, h_in, sizeof(float) * (size_t)B * 64, cudaMemcpyDeviceToDevice, st));
+    else CU(cudaMemsetAsync(h_out, 0, sizeof(float) * (size_t)B * 64, st));
+    return NTM_OK;
+}
+
+int ntm_gru_forward(void* handle, int mode, const float* x, int64_t ldx, float* y, int64_t ldy, const float* h_in,
+                    float* h_out, int64_t B, int64_t T, int skip, void* stream)
+{
+    Handle* hd = as_handle(handle);
+    if (!hd || B < 0 || T < 0) return NTM_EINVAL;
+    if (B == 0) return NTM_OK;
+    if (!h_out) return NTM_EINVAL;
+    DeviceGuard g(hd->device);
+    if (!g.ok) return cuda_fail(cudaErrorInvalidDevice);
+    if (T == 0) return copy_state(h_in, h_out, B, (cudaStream_t)stream);
+    if (!x || !y || ldx < T || ldy < T) return NTM_EINVAL;
+    ntm::GruArgs a{};
+    a.blob = hd->blob; a.x = x; a.y = y; a.h_in = h_in; a.h_out = h_out;
+    a.B = B; a.T = T; a.ldx = ldx; a.ldy = ldy; a.skip = skip;
+    return run_gru(hd, mode, a, (cudaStream_t)stream);
+}
+
+int ntm_diffdel_forward(void* handle, int mode, const float* x, int64_t ldx, const float* d, int64_t ldd, float* y,
+                        int64_t ldy, float* pre_d, int64_t ldp, const float* h_in, float* h_out, const float* hist_in,
+                        float* hist_out, int64_t B, int64_t T, int64_t D, int warmup, int skip, void* stream)
+{
+    Handle* hd = as_handle(handle);
+    if (!hd || B < 0 || T < 0 || D < 0 || D > 0x7fffffff) return NTM_EINVAL;
+    if (B == 0) return NTM_OK;
+    if (!h_out || (D > 0 && (!hist_in || !hist_out || hist_in == hist_out))) return NTM_EINVAL;
+    DeviceGuard g(hd->device);
+    if (!g.ok) return cuda_fail(cudaErrorInvalidDevice);
+    if (T == 0) {                                   // nothing to compute: state and history are unchanged
+        if (D > 0)
+            CU(cudaMemcpyAsync(hist_out, hist_in, sizeof(float) * (size_t)B * (size_t)D, cudaMemcpyDeviceToDevice,
+                               (cudaStream_t)stream));
+        return copy_state(h_in, h_out, B, (cudaStream_t)stream);
+    }
+    if (!x || !d || !y || !pre_d || ldx < T || ldd < T || ldy < T || ldp < T || y == pre_d) return NTM_EINVAL;
+    ntm::GruArgs a{};
+    a.blob = hd->blob; a.x = x; a.y = y; a.h_in = h_in; a.h_out = h_out; a.d = d; a.pre = pre_d;
+    a.hist_in = hist_in; a.hist_out = hist_out;
+    a.B = B; a.T = T; a.ldx = ldx; a.ldy = ldy; a.ldd = ldd; a.ldp = ldp;
+    a.D = (int)D; a.warmup = warmup; a.skip = skip;
+    return run_gru(hd, mode, a, (cudaStream_t)stream);
+}
+
+int ntm_delay_forward(const float* x, int64_t ldx, const float* d, int64_t ldd, float* y, int64_t ldy,
+                      const float* hist_in, float* hist_out, int64_t B, int64_t T, int64_t D, int warmup, int device,
+                      void* stream)
+{
+    if (B < 0 || T < 0 || D < 0 || D > 0x7fffffff) return NTM_EINVAL;
+    if (B == 0) return NTM_OK;
+    if (D > 0 && (!hist_in || !hist_out || hist_in == hist_out)) return NTM_EINVAL;
+    if (T > 0 && (!x || !y || x == y || (!warmup && !d) || ldx < T || ldy < T || (d && ldd < T))) return NTM_EINVAL;
+    DeviceGuard g(device);
+    if (!g.ok) return cuda_fail(cudaErrorInvalidDevice);
+    CU(ntm::launch_delay(x, ldx, d, ldd, y, ldy, hist_in, hist_out, B, T, D, warmup, (cudaStream_t)stream));
+    return NTM_OK;
+}
+
+int ntm_delay_check(const float* d, int64_t ldd, int64_t B, int64_t T, int64_t D, int device, void* stream)
+{
+    if (B < 0 || T < 0 || D < 0) return NTM_EINVAL;
+    if (B == 0 || T == 0) return NTM_OK;
+    if (!d || ldd < T) return NTM_EINVAL;
+    DeviceGuard g(device);
+    if (!g.ok) return cuda_fail(cudaErrorInvalidDevice);
+    int* flag = nullptr;
+    CU(cudaMalloc(&flag, sizeof(int)));
+    int host_flag = 0;
+    cudaError_t e = cudaMemsetAsync(flag, 0, sizeof(int), (cudaStream_t)stream);
+    if (e == cudaSuccess) e = ntm::launch_delay_check(d, ldd, B, T, D, flag, (cudaStream_t)stream);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(&host_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+    cudaFree(flag);
+    if (e != cudaSuccess) return cuda_fail(e);
+    return host_flag ? NTM_EDELAY : NTM_OK;
+}
+
+int ntm_gru_predict_host(void* handle, int mode, const float* x_host, float* y_host, float* h_host, int64_t B,
+                         int64_t T, int skip, int64_t chunk_T)
+{
+    Handle* hd = as_handle(handle);
+    if (!hd) return NTM_EINVAL;
+    return predict_host(hd, mode, x_host, nullptr, y_host, nullptr, h_host, nullptr, B, T, 0, skip, chunk_T);
+}
+
+int ntm_diffdel_predict_host(void* handle, int mode, const float* x_host, const float* d_host, float* y_host,
+                             float* pre_d_host, float* h_host, float* hist_host, int64_t B, int64_t T, int64_t D,
+                             int skip, int64_t chunk_T)
+{
+    Handle* hd = as_handle(handle);
+    if (!hd || !d_host) return NTM_EINVAL;
+    return predict_host(hd, mode, x_host, d_host, y_host, pre_d_host, h_host, hist_host, B, T, D, skip, chunk_T);
+}
+
+}  // extern "C"

@@ -1,0 +1,78 @@
+// Shared declarations of the engine's translation units (internal; the public ABI is include/ntm_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ntm {
+
+constexpr int H64 = 64;      // hidden size all shipped checkpoints use
+constexpr int G192 = 192;    // 3 gates x 64, row order r,z,n (torch rnn.py:1221-1224)
+
+// Device parameter blob (floats), written once by ntm_gru_prepare.
+struct BlobLayout {
+    static constexpr int W_HH = 0;                    // 192 x 64, PyTorch layout
+    static constexpr int W_IH = W_HH + G192 * H64;    // 192
+    static constexpr int B_IH = W_IH + G192;          // 192
+    static constexpr int B_HH = B_IH + G192;          // 192
+    static constexpr int W_OUT = B_HH + G192;         // 64
+    static constexpr int B_OUT = W_OUT + H64;         // 1 (0 when the head has no bias)
+    static constexpr int FP32_END = B_OUT + 4;
+};
+
+// Arguments of one recurrent launch; d == nullptr selects the plain RNN.forward path.
+struct GruArgs {
+    const float* blob;
+    const float* x;
+    float* y;
+    const float* h_in;      // B x 64 or nullptr (zero state)
+    float* h_out;           // B x 64 (may alias h_in)
+    const float* d;         // delay trajectory (samples) or nullptr
+    float* pre;             // GRU head output before the delay (DiffDelRNN only)
+    const float* hist_in;   // B x D
+    float* hist_out;        // B x D
+    long long B, T, ldx, ldy, ldd, ldp;
+    int D;
+    int warmup;
+    int skip;
+};
+
+// per-TU launchers -------------------------------------------------------------------------------
+cudaError_t launch_gru_fp32(const GruArgs& a, int sm_count, int tune_s, int tune_ks, cudaStream_t st);
+cudaError_t launch_delay(const float* x, long long ldx, const float* d, long long ldd, float* y, long long ldy,
+                         const float* hist_in, float* hist_out, long long B, long long T, long long D, int warmup,
+                         cudaStream_t st);
+cudaError_t launch_delay_check(const float* d, long long ldd, long long B, long long T, long long D, int* flag_dev,
+                               cudaStream_t st);
+
+extern unsigned long long g_launches;   // engine kernels launched by this process (ntm_query)
+
+// ------------------------------------------------------------------------------------------------
+// Fractional delay read shared by the fused and the stand-alone kernels.
+// Reference: TimeVaryingDelayLine.forward, code/model.py:294-311 -- weights relu(1 - |j - d|) over the taps
+// j = 0..D; only j = floor(d) and floor(d)+1 can be non-zero.  Weights and products are rounded exactly as
+// the reference rounds them (float sub/abs/sub, float mul, one float add) so the result is bit-identical.
+template <class LoadPast>
+__device__ __forceinline__ float delay_read(float dt, long long t, int D, LoadPast past)
+{
+    const float fl = floorf(dt);
+    float acc = 0.0f;
+#pragma unroll
+    for (int tap = 1; tap >= 0; --tap) {
+        const float jf = fl + (float)tap;
+        if (jf >= 0.0f && jf <= (float)D) {
+            const float w = fmaxf(__fsub_rn(1.0f, fabsf(__fsub_rn(jf, dt))), 0.0f);
+            acc = __fadd_rn(acc, __fmul_rn(w, past(t - (long long)jf)));
+        }
+    }
+    return acc;
+}
+
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+}  // namespace ntm

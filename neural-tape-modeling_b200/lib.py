@@ -1,0 +1,67 @@
+"""ctypes binding of libntm_b200.so -- every symbol include/ntm_b200.h declares, nothing else.
+
+There is NO fallback: if the library is missing or a call fails, a RuntimeError is raised.
+"""
+import ctypes
+import os
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "libntm_b200.so")
+
+MODE_FP32, MODE_TF32, MODE_BF16, MODE_TF32X3 = 0, 1, 2, 3
+MODES = {"fp32": MODE_FP32, "tf32": MODE_TF32, "bf16": MODE_BF16, "tf32x3": MODE_TF32X3}
+Q_VERSION, Q_DEVICE_COUNT, Q_SM_COUNT, Q_MODE_MASK, Q_KERNEL_LAUNCHES = 0, 1, 2, 3, 4
+E_DELAY = -5
+
+_vp = ctypes.c_void_p
+_i64 = ctypes.c_int64
+_int = ctypes.c_int
+
+# name -> (restype, argtypes): must list exactly the functions of include/ntm_b200.h
+SIGNATURES = {
+    "ntm_query": (_int, [_int]),
+    "ntm_strerror": (ctypes.c_char_p, [_int]),
+    "ntm_last_cuda_error": (_int, []),
+    "ntm_gru_prepare": (_int, [_vp] * 6 + [_int, _int, ctypes.POINTER(_vp)]),
+    "ntm_destroy": (None, [_vp]),
+    "ntm_gru_forward": (_int, [_vp, _int, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _i64, _int, _vp]),
+    "ntm_diffdel_forward": (_int, [_vp, _int, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp,
+                                   _i64, _i64, _i64, _int, _int, _vp]),
+    "ntm_delay_forward": (_int, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _int, _int, _vp]),
+    "ntm_delay_check": (_int, [_vp, _i64, _i64, _i64, _i64, _int, _vp]),
+    "ntm_gru_predict_host": (_int, [_vp, _int, _vp, _vp, _vp, _i64, _i64, _int, _i64]),
+    "ntm_diffdel_predict_host": (_int, [_vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _i64]),
+    "ntm_set_tuning": (_int, [_int, _int]),
+}
+
+_lib = None
+
+
+def load():
+    """dlopen the in-tree library (build it with `python neural-tape-modeling_b200/build.py`)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: build it first (python neural-tape-modeling_b200/build.py); "
+                               "ntm_b200 has no fallback path")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc):
+    """0 -> None; NTM_EDELAY -> AssertionError (the reference asserts, code/model.py:283); else RuntimeError."""
+    if rc == 0:
+        return
+    msg = load().ntm_strerror(rc).decode()
+    if rc == E_DELAY:
+        raise AssertionError(msg)
+    raise RuntimeError(f"ntm_b200: {msg} (code {rc})")
+
+
+def query(what):
+    return load().ntm_query(what)

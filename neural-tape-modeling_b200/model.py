@@ -1,0 +1,331 @@
+"""Drop-in replacements for the three hot-path classes of the reference's code/model.py:
+
+    RNN                    code/model.py:20-246    (forward / predict / warm_start / hidden handling)
+    TimeVaryingDelayLine   code/model.py:249-332
+    DiffDelRNN             code/model.py:335-653
+
+Same constructor arguments, attribute names, state_dict keys and method signatures, so
+`from model import RNN, DiffDelRNN, TimeVaryingDelayLine` in code/test-model.py:29 can point here.
+All arithmetic runs in libntm_b200.so (hand-written sm_100a CUDA) through the C ABI of
+include/ntm_b200.h; torch only owns the memory and the stream.  There is no CPU path and no
+torch.nn.GRU fallback: tensors must live on a CUDA device, otherwise a RuntimeError is raised.
+Training (train_epoch / validate, code/model.py:90-216, :426-616) is out of scope.
+
+Deliberate differences from the reference:
+  * the device is the input tensor's device, not the global "cuda" (needed to shard streams over 8 GPUs);
+  * predict() accepts B > 1 streams: the batch-1 warm state (and silence-response delay history) is broadcast,
+    which equals B separate reference predict() calls; it runs ONE persistent launch instead of 2048-sample
+    segments (the recurrence is segmentation-invariant);
+  * forward() rejects C != 1 channels (the reference's reshape is only a transpose when C == 1).
+"""
+import ctypes
+import weakref
+
+import torch
+
+from . import lib as _lib
+
+WARM_LEN = 2 ** 10      # code/model.py:60, :386
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _as_rows(t, name):
+    """(B, 1, T) tensor -> float32 view with unit stride in T; returns (tensor, B, T, ld)."""
+    if t.dim() != 3 or t.shape[1] != 1:
+        raise RuntimeError(f"{name}: expected shape (N_BATCHES, 1, N_SAMPLES), got {tuple(t.shape)}")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: ntm_b200 has no CPU path; move the tensor to a CUDA device")
+    if t.dtype != torch.float32:
+        t = t.float()                                   # code/model.py:76, :403 (f64 -> f32)
+    if t.shape[2] > 1 and t.stride(2) != 1:
+        t = t.contiguous()
+    B, T = t.shape[0], t.shape[2]
+    ld = t.stride(0) if B > 1 else max(T, 1)
+    if B > 1 and ld < T:
+        t = t.contiguous()
+        ld = T
+    return t, B, T, ld
+
+
+class _Engine:
+    """Owns the packed-parameter handle of one module on one device; re-prepared when parameters change."""
+
+    def __init__(self):
+        self.handle = None
+        self.key = None
+        self._finalizer = None
+
+    def get(self, gru, head, device):
+        params = [gru.weight_ih_l0, gru.weight_hh_l0, gru.bias_ih_l0, gru.bias_hh_l0, head.weight, head.bias]
+        key = (device.index,) + tuple((p.data_ptr(), p._version) if p is not None else None for p in params)
+        if key != self.key:
+            self.release()
+            host = [None if p is None else p.detach().to("cpu", torch.float32).contiguous() for p in params]
+            H = host[1].shape[1]
+            if host[0].shape[1] != 1 or head.weight.shape[0] != 1:
+                raise RuntimeError("ntm_b200: only input_size=1, output_size=1 models are supported")
+            handle = ctypes.c_void_p()
+            rc = _lib.load().ntm_gru_prepare(*[_ptr(t) for t in host], H, device.index, ctypes.byref(handle))
+            _lib.check(rc)
+            self.handle, self.key = handle, key
+            self._finalizer = weakref.finalize(self, _lib.load().ntm_destroy, handle)
+        return self.handle
+
+    def __deepcopy__(self, memo):          # handles are per-object; a copied module re-prepares lazily
+        return _Engine()
+
+    def __reduce__(self):
+        return (_Engine, ())
+
+    def release(self):
+        if self._finalizer is not None:
+            self._finalizer()
+            self._finalizer = None
+        self.handle, self.key = None, None
+
+
+class RNN(torch.nn.Module):
+    """GRU(1 -> hidden) + Linear(hidden -> 1) tape nonlinearity; mirrors code/model.py:20-246."""
+
+    _head_bias = True
+
+    def __init__(self, input_size=1, hidden_size=8, output_size=1, skip=False):
+        super().__init__()
+        self.input_size = input_size
+        self.hidden_size = hidden_size
+        self.output_size = output_size
+        self.skip = skip
+        # parameter containers only (state_dict keys GRU.* / output.*); their forward() is never called
+        self.GRU = torch.nn.GRU(input_size, hidden_size, batch_first=True)
+        self.output = torch.nn.Linear(hidden_size, output_size, bias=self._head_bias)
+        self.mode = "fp32"          # "fp32" | "tf32" | "bf16" | "tf32x3"  (include/ntm_b200.h NTM_MODE_*)
+        self._engine = _Engine()
+        self.hidden = None
+
+    # -- state handling (code/model.py:50-56) ---------------------------------------------------
+    def initialize_hidden(self):
+        self.hidden = None
+
+    def detach_hidden(self):
+        self.hidden = self.hidden.clone().detach()
+
+    def _device(self):
+        return self.GRU.weight_hh_l0.device
+
+    def _handle(self, device):
+        if self._device() != device:
+            raise RuntimeError(f"input is on {device} but the model parameters are on {self._device()}")
+        return self._engine.get(self.GRU, self.output, device)
+
+    def _hidden_in(self, B, device):
+        h = self.hidden
+        if h is None:
+            return None
+        if tuple(h.shape) != (1, B, self.hidden_size):
+            raise RuntimeError(f"Expected hidden size (1, {B}, {self.hidden_size}), got {list(h.shape)}")
+        if h.device != device or h.dtype != torch.float32 or not h.is_contiguous():
+            h = h.to(device, torch.float32).contiguous()
+        return h
+
+    def warm_start(self):
+        """1024 samples of silence from the current state, batch 1 (code/model.py:58-65)."""
+        with torch.no_grad():
+            self(torch.zeros((1, 1, WARM_LEN), device=self._device()))
+
+    def forward(self, x):
+        """x (N_BATCHES, 1, N_SAMPLES) -> y of the same shape; carries self.hidden (code/model.py:67-88)."""
+        x, B, T, ldx = _as_rows(x, "x")
+        dev = x.device
+        handle = self._handle(dev)
+        h_in = self._hidden_in(B, dev)
+        y = torch.empty((B, 1, T), dtype=torch.float32, device=dev)
+        h_out = torch.empty((1, B, self.hidden_size), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            rc = _lib.load().ntm_gru_forward(handle, _lib.MODES[self.mode], _ptr(x), ldx, _ptr(y), max(T, 1),
+                                             _ptr(h_in), _ptr(h_out), B, T, int(bool(self.skip)), _stream(dev))
+        _lib.check(rc)
+        self.hidden = h_out
+        return y
+
+    def predict(self, input):
+        """Zero state -> warm start -> whole signal (code/model.py:218-246), for any number of streams."""
+        dev = self._device()
+        input = input.to(dev)
+        self.initialize_hidden()
+        self.warm_start()
+        B = input.shape[0]
+        if B != 1:
+            self.hidden = self.hidden.expand(1, B, self.hidden_size).contiguous()
+        return self.forward(input)
+
+    def predict_host(self, input, chunk=0):
+        """predict() for a HOST tensor (pinned for full speed): chunked H2D / kernel / D2H pipeline inside the
+        engine (ntm_gru_predict_host).  Returns a pinned host tensor.  This is the end-to-end call the bench times
+        (host->device at code/test-model.py:427-433, device->host at :525)."""
+        if input.is_cuda or input.dim() != 3 or input.shape[1] != 1:
+            raise RuntimeError("predict_host expects a host tensor of shape (N_BATCHES, 1, N_SAMPLES)")
+        dev = self._device()
+        handle = self._handle(dev)
+        x = input.float().contiguous()
+        B, T = x.shape[0], x.shape[2]
+        self.initialize_hidden()
+        self.warm_start()
+        h = self.hidden.reshape(1, self.hidden_size).expand(B, self.hidden_size).contiguous().cpu()
+        y = torch.empty((B, 1, T), dtype=torch.float32, pin_memory=True)
+        rc = _lib.load().ntm_gru_predict_host(handle, _lib.MODES[self.mode], _ptr(x), _ptr(y), _ptr(h), B, T,
+                                              int(bool(self.skip)), int(chunk))
+        _lib.check(rc)
+        self.hidden = h.reshape(1, B, self.hidden_size).to(dev)
+        return y
+
+
+class TimeVaryingDelayLine(torch.nn.Module):
+    """Feed-forward linear-interpolation delay line with carried history; mirrors code/model.py:249-332."""
+
+    def __init__(self, max_delay=40000, channels=1):
+        super().__init__()
+        self.max_delay = max_delay
+        self.check_delay = True     # keep the reference's assert (costs one stream sync per call)
+        # plain attribute, not a registered buffer: stays out of state_dict (code/model.py:267)
+        self.buffer = torch.zeros(2, channels, max_delay)
+
+    def _history(self, B, device):
+        buf = self.buffer
+        if buf.dim() != 3 or buf.shape[0] != B or buf.shape[1] != 1:
+            raise RuntimeError(f"Sizes of tensors must match: delay buffer {list(buf.shape)} vs batch {B}")
+        if buf.shape[2] != self.max_delay:
+            raise RuntimeError(f"delay buffer length {buf.shape[2]} != max_delay {self.max_delay}")
+        if buf.device != device or buf.dtype != torch.float32 or not buf.is_contiguous():
+            buf = buf.to(device, torch.float32).contiguous()
+        return buf
+
+    def _check(self, d, ldd, B, T, device):
+        if self.check_delay and T > 0:
+            _lib.check(_lib.load().ntm_delay_check(_ptr(d), ldd, B, T, int(self.max_delay), device.index,
+                                                   _stream(device)))
+
+    def forward(self, x, dt, warmup=False):
+        """x, dt (N_BATCHES, 1, N_SAMPLES), dt in samples -> delayed x (code/model.py:269-320)."""
+        x, B, T, ldx = _as_rows(x, "x")
+        dt, Bd, Td, ldd = _as_rows(dt.to(x.device), "dt")
+        if (Bd, Td) != (B, T):
+            raise RuntimeError(f"x {tuple(x.shape)} and dt {tuple(dt.shape)} must have the same shape")
+        dev = x.device
+        hist = self._history(B, dev)
+        D = int(self.max_delay)
+        with torch.cuda.device(dev):
+            self._check(dt, ldd, B, T, dev)
+            y = torch.empty((B, 1, T), dtype=torch.float32, device=dev)
+            hist_out = torch.empty((B, 1, D), dtype=torch.float32, device=dev)
+            rc = _lib.load().ntm_delay_forward(_ptr(x), ldx, _ptr(dt), ldd, _ptr(y), max(T, 1), _ptr(hist),
+                                               _ptr(hist_out), B, T, D, int(bool(warmup)), dev.index, _stream(dev))
+        _lib.check(rc)
+        self.buffer = hist_out
+        return y
+
+    def detach_buffer(self):
+        self.buffer = self.buffer.clone().detach()
+
+    def init_buffer(self, N, max_d=None):
+        """Zero history for N streams (code/model.py:326-332).  max_d defaults to the current max_delay so that
+        apply_delay's one-argument call (code/test-model.py:268) works."""
+        if max_d is not None:
+            self.max_delay = max_d
+        device = torch.device("cuda") if torch.cuda.is_available() else torch.device("cpu")
+        self.buffer = torch.zeros(N, 1, self.max_delay, device=device)
+
+
+class DiffDelRNN(RNN):
+    """GRU + bias-free Linear head + time-varying delay line; mirrors code/model.py:335-653."""
+
+    _head_bias = False
+
+    def __init__(self, input_size=1, hidden_size=8, output_size=1, skip=False, max_delay=10000):
+        super().__init__(input_size, hidden_size, output_size, skip)
+        self.max_delay = max_delay
+        self.diffdel = TimeVaryingDelayLine(max_delay=max_delay)
+        self.initialize_hidden(2, max_delay)
+
+    def initialize_hidden(self, N=2, max_D=None):
+        """Zero state and a zero delay history of length int(max_D)+1 (code/model.py:372-375)."""
+        self.hidden = None
+        if hasattr(self, "diffdel"):
+            self.diffdel.init_buffer(N, int(self.max_delay if max_D is None else max_D) + 1)
+
+    def detach_hidden(self):
+        super().detach_hidden()
+        self.diffdel.detach_buffer()
+
+    def warm_start(self):
+        """GRU + delay line on 1024 samples of silence with zero delay, batch 1 (code/model.py:377-391)."""
+        with torch.no_grad():
+            z = torch.zeros((1, 1, WARM_LEN), device=self._device())
+            self(z, z.clone())
+
+    def forward(self, x, del_traj, warmup=False):
+        """-> (y, pre_d): GRU head output before and after the delay (code/model.py:393-424)."""
+        x, B, T, ldx = _as_rows(x, "x")
+        dev = x.device
+        d, Bd, Td, ldd = _as_rows(del_traj.to(dev), "del_traj")
+        if (Bd, Td) != (B, T):
+            raise RuntimeError(f"x {tuple(x.shape)} and del_traj {tuple(d.shape)} must have the same shape")
+        handle = self._handle(dev)
+        h_in = self._hidden_in(B, dev)
+        hist = self.diffdel._history(B, dev)
+        D = int(self.diffdel.max_delay)
+        with torch.cuda.device(dev):
+            self.diffdel._check(d, ldd, B, T, dev)
+            y = torch.empty((B, 1, T), dtype=torch.float32, device=dev)
+            pre_d = torch.empty((B, 1, T), dtype=torch.float32, device=dev)
+            h_out = torch.empty((1, B, self.hidden_size), dtype=torch.float32, device=dev)
+            hist_out = torch.empty((B, 1, D), dtype=torch.float32, device=dev)
+            rc = _lib.load().ntm_diffdel_forward(handle, _lib.MODES[self.mode], _ptr(x), ldx, _ptr(d), ldd, _ptr(y),
+                                                 max(T, 1), _ptr(pre_d), max(T, 1), _ptr(h_in), _ptr(h_out),
+                                                 _ptr(hist), _ptr(hist_out), B, T, D, int(bool(warmup)),
+                                                 int(bool(self.skip)), _stream(dev))
+        _lib.check(rc)
+        self.hidden = h_out
+        self.diffdel.buffer = hist_out
+        return y, pre_d
+
+    def predict(self, input, d_traj):
+        """-> (output, output_pre_d) (code/model.py:618-653), for any number of streams."""
+        dev = self._device()
+        input, d_traj = input.to(dev), d_traj.to(dev)
+        B = input.shape[0]
+        self.initialize_hidden(1, self.max_delay)
+        self.warm_start()
+        if B != 1:
+            self.hidden = self.hidden.expand(1, B, self.hidden_size).contiguous()
+            self.diffdel.buffer = self.diffdel.buffer.expand(B, 1, -1).contiguous()
+        return self.forward(input, d_traj)
+
+    def predict_host(self, input, d_traj, chunk=0):
+        """predict() for HOST tensors through ntm_diffdel_predict_host; returns pinned host (output, output_pre_d)."""
+        if input.is_cuda or d_traj.is_cuda or input.dim() != 3 or input.shape[1] != 1:
+            raise RuntimeError("predict_host expects host tensors of shape (N_BATCHES, 1, N_SAMPLES)")
+        dev = self._device()
+        handle = self._handle(dev)
+        x = input.float().contiguous()
+        d = d_traj.float().contiguous()
+        B, T = x.shape[0], x.shape[2]
+        self.initialize_hidden(1, self.max_delay)
+        self.warm_start()
+        D = int(self.diffdel.max_delay)
+        h = self.hidden.reshape(1, self.hidden_size).expand(B, self.hidden_size).contiguous().cpu()
+        hist = self.diffdel.buffer.reshape(1, D).expand(B, D).contiguous().cpu()
+        y = torch.empty((B, 1, T), dtype=torch.float32, pin_memory=True)
+        pre = torch.empty((B, 1, T), dtype=torch.float32, pin_memory=True)
+        rc = _lib.load().ntm_diffdel_predict_host(handle, _lib.MODES[self.mode], _ptr(x), _ptr(d), _ptr(y), _ptr(pre),
+                                                  _ptr(h), _ptr(hist), B, T, D, int(bool(self.skip)), int(chunk))
+        _lib.check(rc)
+        self.hidden = h.reshape(1, B, self.hidden_size).to(dev)
+        self.diffdel.buffer = hist.reshape(B, 1, D).to(dev)
+        return y, pre
