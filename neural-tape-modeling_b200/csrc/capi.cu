@@ -14,7 +14,7 @@ namespace {
 
 constexpr unsigned HANDLE_MAGIC = 0x4e544d42u;   // "NTMB"
 thread_local int t_last_cuda = 0;
-int g_tune_s = 0, g_tune_ks = 0;
+int g_tune_s = 0, g_tune_ks = 0, g_tune_fast = 0;
 
 struct HostPipe {            // staging of the *_host entry points
     cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
@@ -66,7 +66,7 @@ bool mode_supported(int mode) { return mode == NTM_MODE_FP32; }
 int run_gru(Handle* hd, int mode, const ntm::GruArgs& a, cudaStream_t st)
 {
     if (!mode_supported(mode)) return NTM_EUNSUPPORTED;
-    CU(ntm::launch_gru_fp32(a, hd->sm_count, g_tune_s, g_tune_ks, st));
+    CU(ntm::launch_gru_fp32(a, hd->sm_count, g_tune_s, g_tune_ks & 0xff, g_tune_fast, st));
     return NTM_OK;
 }
 
@@ -227,7 +227,8 @@ int ntm_set_tuning(int streams_per_cta, int ksplit)
 {
     if (streams_per_cta < 0 || ksplit < 0) return NTM_EINVAL;
     g_tune_s = streams_per_cta;
-    g_tune_ks = ksplit;
+    g_tune_ks = ksplit & 0xff;
+    g_tune_fast = (ksplit >> 8) & 1;      // experiment: bit 8 selects the MUFU-approx activations
     return NTM_OK;
 }
 

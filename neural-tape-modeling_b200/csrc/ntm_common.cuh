@@ -37,7 +37,7 @@ struct GruArgs {
 };
 
 // per-TU launchers -------------------------------------------------------------------------------
-cudaError_t launch_gru_fp32(const GruArgs& a, int sm_count, int tune_s, int tune_ks, cudaStream_t st);
+cudaError_t launch_gru_fp32(const GruArgs& a, int sm_count, int tune_s, int tune_ks, int fast_act, cudaStream_t st);
 cudaError_t launch_delay(const float* x, long long ldx, const float* d, long long ldd, float* y, long long ldy,
                          const float* hist_in, float* hist_out, long long B, long long T, long long D, int warmup,
                          cudaStream_t st);
@@ -65,6 +65,19 @@ __device__ __forceinline__ float delay_read(float dt, long long t, int D, LoadPa
         }
     }
     return acc;
+}
+
+__device__ __forceinline__ float ex2_approx(float x)
+{
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x)
+{
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 
 __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src)

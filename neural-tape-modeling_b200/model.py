@@ -54,6 +54,13 @@ def _as_rows(t, name):
     return t, B, T, ld
 
 
+def _version(p):
+    try:
+        return p._version
+    except RuntimeError:            # inference tensors carry no version counter
+        return -1
+
+
 class _Engine:
     """Owns the packed-parameter handle of one module on one device; re-prepared when parameters change."""
 
@@ -64,7 +71,7 @@ class _Engine:
 
     def get(self, gru, head, device):
         params = [gru.weight_ih_l0, gru.weight_hh_l0, gru.bias_ih_l0, gru.bias_hh_l0, head.weight, head.bias]
-        key = (device.index,) + tuple((p.data_ptr(), p._version) if p is not None else None for p in params)
+        key = (device.index,) + tuple((p.data_ptr(), _version(p)) if p is not None else None for p in params)
         if key != self.key:
             self.release()
             host = [None if p is None else p.detach().to("cpu", torch.float32).contiguous() for p in params]
@@ -108,6 +115,12 @@ class RNN(torch.nn.Module):
         self.mode = "fp32"          # "fp32" | "tf32" | "bf16" | "tf32x3"  (include/ntm_b200.h NTM_MODE_*)
         self._engine = _Engine()
         self.hidden = None
+        # parameters are re-packed lazily whenever they may have changed
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module._engine.release())
+
+    def _apply(self, fn, *args, **kwargs):      # .to() / .cuda() / .float() ...
+        self._engine.release()
+        return super()._apply(fn, *args, **kwargs)
 
     # -- state handling (code/model.py:50-56) ---------------------------------------------------
     def initialize_hidden(self):
