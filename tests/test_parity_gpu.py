@@ -119,6 +119,7 @@ def test_rnn_streams_are_independent_bit_exact():
     B, T = 37, 1500
     x = dev(signals.stream_batch(B, T)).reshape(B, 1, T)
     with torch.inference_mode():
+        lib.load().ntm_set_tuning(1, 4)                # same k-split as the batched runs below
         singles = torch.cat([m.predict(x[b:b + 1]) for b in range(B)], 0)
         for s in (0, 1, 2, 4, 8, 16):
             lib.load().ntm_set_tuning(s, 4)
