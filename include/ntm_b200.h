@@ -45,7 +45,8 @@ extern "C" {
 #define NTM_MODE_FP32     0     /* fp32 FFMA on CUDA cores, libm-grade activations: the parity anchor */
 #define NTM_MODE_TF32     1     /* tensor cores, tf32 operands, fp32 accumulate */
 #define NTM_MODE_BF16     2     /* tensor cores, bf16 operands, fp32 accumulate (opt-in, lower accuracy) */
-#define NTM_MODE_TF32X3   3     /* tensor cores, 3xTF32 split (fp32-grade result) */
+#define NTM_MODE_TF32X3   3     /* tensor cores, 3xTF32 split (fp32-grade result) -- reserved, not built yet */
+#define NTM_MODE_F16      4     /* tensor cores, f16 operands (11-bit significand like tf32, half the MMAs), fp32 acc. */
 
 /* ntm_query selectors */
 #define NTM_Q_VERSION        0
@@ -117,7 +118,8 @@ int ntm_diffdel_predict_host(void* handle, int mode, const float* x_host, const 
                              float* y_host, float* pre_d_host, float* h_host, float* hist_host,
                              int64_t B, int64_t T, int64_t D, int skip, int64_t chunk_T);
 
-/* Tuning knob for experiments: streams per CTA / k-split of the fp32 kernel (0 = automatic). */
+/* Tuning knob for experiments (0 = automatic).  fp32 kernel: streams per CTA / k-split.  Tensor-core kernel:
+ * streams per group (8, 16, 32, 64) / groups per CTA (1, 2). */
 int ntm_set_tuning(int streams_per_cta, int ksplit);
 
 #if defined(__GNUC__)

@@ -15,6 +15,7 @@ namespace {
 constexpr unsigned HANDLE_MAGIC = 0x4e544d42u;   // "NTMB"
 thread_local int t_last_cuda = 0;
 int g_tune_s = 0, g_tune_ks = 0, g_tune_fast = 0;
+long long g_mma_streams_per_sm = 1ll << 40;   // crossover between the two tensor-core kernels (measured)
 
 struct HostPipe {            // staging of the *_host entry points
     cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
@@ -61,12 +62,27 @@ Handle* as_handle(void* p)
     return (h && h->magic == HANDLE_MAGIC) ? h : nullptr;
 }
 
-bool mode_supported(int mode) { return mode == NTM_MODE_FP32; }
+constexpr int MODE_MASK = (1 << NTM_MODE_FP32) | (1 << NTM_MODE_TF32) | (1 << NTM_MODE_BF16) | (1 << NTM_MODE_F16);
+bool mode_supported(int mode) { return mode >= 0 && mode < 31 && ((MODE_MASK >> mode) & 1); }
 
 int run_gru(Handle* hd, int mode, const ntm::GruArgs& a, cudaStream_t st)
 {
     if (!mode_supported(mode)) return NTM_EUNSUPPORTED;
-    CU(ntm::launch_gru_fp32(a, hd->sm_count, g_tune_s, g_tune_ks & 0xff, g_tune_fast, st));
+    if (mode == NTM_MODE_FP32) {
+        CU(ntm::launch_gru_fp32(a, hd->sm_count, g_tune_s, g_tune_ks & 0xff, g_tune_fast, st));
+    } else {
+        const int fmt = mode == NTM_MODE_TF32 ? 2 : mode == NTM_MODE_BF16 ? 1 : 0;    // tc_prims.cuh FMT_*
+        // latency regime (few streams per SM): warp-level mma.sync kernel; throughput regime: tcgen05 kernel.
+        // ntm_set_tuning(n, 3) forces the former with n/8 tiles per CTA, (n, 1|2) the latter.
+        const int tg = g_tune_ks & 0xff;
+        const bool use_mma = tg == 3 || (tg == 0 && a.B <= (long long)hd->sm_count * g_mma_streams_per_sm);
+        if (use_mma) {
+            const int nt = g_tune_s > 0 && tg == 3 ? g_tune_s / 8 : 1;
+            CU(ntm::launch_gru_mma(a, fmt, nt, st));
+        } else {
+            CU(ntm::launch_gru_tc(a, fmt, hd->sm_count, tg ? g_tune_s : 0, tg, st));
+        }
+    }
     return NTM_OK;
 }
 
@@ -201,7 +217,7 @@ int ntm_query(int what)
             }
             return n;
         }
-        case NTM_Q_MODE_MASK: return 1 << NTM_MODE_FP32;
+        case NTM_Q_MODE_MASK: return MODE_MASK;
         case NTM_Q_KERNEL_LAUNCHES: return (int)(ntm::g_launches & 0x7fffffffull);
         default: return NTM_EINVAL;
     }
@@ -249,15 +265,16 @@ int ntm_gru_prepare(const float* w_ih, const float* w_hh, const float* b_ih, con
     if (!g.ok) return cuda_fail(cudaErrorInvalidDevice);
 
     using L = ntm::BlobLayout;
-    float* host = new (std::nothrow) float[L::FP32_END];
+    float* host = new (std::nothrow) float[L::TOTAL];
     if (!host) return NTM_ENOMEM;
-    memset(host, 0, sizeof(float) * L::FP32_END);
+    memset(host, 0, sizeof(float) * L::TOTAL);
     memcpy(host + L::W_HH, w_hh, sizeof(float) * ntm::G192 * ntm::H64);
     memcpy(host + L::W_IH, w_ih, sizeof(float) * ntm::G192);
     memcpy(host + L::B_IH, b_ih, sizeof(float) * ntm::G192);
     memcpy(host + L::B_HH, b_hh, sizeof(float) * ntm::G192);
     memcpy(host + L::W_OUT, w_out, sizeof(float) * ntm::H64);
     host[L::B_OUT] = b_out ? b_out[0] : 0.0f;
+    ntm::pack_tc_images(w_hh, host);
 
     Handle* hd = new (std::nothrow) Handle();
     if (!hd) { delete[] host; return NTM_ENOMEM; }
@@ -266,8 +283,8 @@ int ntm_gru_prepare(const float* w_ih, const float* w_hh, const float* b_ih, con
     hd->has_bias = b_out != nullptr;
     hd->blob = nullptr;
     cudaError_t e = cudaDeviceGetAttribute(&hd->sm_count, cudaDevAttrMultiProcessorCount, device);
-    if (e == cudaSuccess) e = cudaMalloc(&hd->blob, sizeof(float) * L::FP32_END);
-    if (e == cudaSuccess) e = cudaMemcpy(hd->blob, host, sizeof(float) * L::FP32_END, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&hd->blob, sizeof(float) * L::TOTAL);
+    if (e == cudaSuccess) e = cudaMemcpy(hd->blob, host, sizeof(float) * L::TOTAL, cudaMemcpyHostToDevice);
     delete[] host;
     if (e != cudaSuccess) {
         if (hd->blob) cudaFree(hd->blob);

@@ -1,0 +1,352 @@
+// Warp-level tensor-core persistent GRU kernel (mma.sync, accumulators in registers) -- the LATENCY regime of the
+// batched path: a few streams per SM (BASELINE cfg 2: 1024 streams over 148 SMs, cfg 3: 256 streams).
+//
+// Why not tcgen05 here: measured on B200 (profiles/r01_tc_probe.txt) a tcgen05.mma costs >= ~40 clk of tensor pipe
+// however small N is, and the issue -> commit -> mbarrier -> tcgen05.ld hand-off adds ~220 clk, so one GRU step
+// through TMEM cannot go below ~700 clk before the gates are even touched; a dependent chain of four
+// mma.sync.m16n8k16 takes ~80 clk with the accumulators already in the registers that evaluate the gates.
+// The tcgen05 kernel (gru_tc.cu) takes over once an SM owns enough streams to be throughput-bound.
+//
+// Replaces the same reference arithmetic as the other kernels: `self.GRU(x, self.hidden)` + `self.output(x)` of
+// RNN.forward / DiffDelRNN.forward (code/model.py:81-82, :412-413; torch rnn.py:1221-1224) and the delay read
+// of code/model.py:422.
+//
+// One CTA = 4 warps owns 8*NT streams for all T steps.  Warp w owns hidden units [16w, 16w+16): three m16 tiles
+//   tile A rows 0-7: r of units 16w+0..7, rows 8-15: z of the same units      -> c0,c1 = r   c2,c3 = z   (unit u0)
+//   tile B the same for units 16w+8..15                                          -> c0,c1 = r   c2,c3 = z   (unit u1)
+//   tile C rows 0-7: n of units 16w+0..7, rows 8-15: n of units 16w+8..15        -> c0,c1 = n(u0) c2,c3 = n(u1)
+// so thread (gid = lane/4, tig = lane%4) ends up with r, z, n of units u0 = 16w+gid, u1 = u0+8 for streams 2tig,
+// 2tig+1 of every n8 tile: no cross-thread exchange between the MMA and the gates.  W_hh fragments stay in registers
+// for the whole kernel (pre-scaled by -log2 e / 2 log2 e, rounded once to the operand format).  The rounded state
+// lives in a double-buffered shared-memory tile laid out so that each thread fetches all its B fragments of a step
+// with two (f16/bf16) or four (tf32) LDS.128; the fp32 state never leaves registers.  One __syncthreads per step.
+#include "ntm_common.cuh"
+#include "tc_prims.cuh"
+
+namespace ntm {
+
+using namespace tc;
+
+namespace {
+
+constexpr float LOG2E_F = 1.4426950408889634f;
+
+template <int FMT>
+struct Frag {
+    static constexpr int ELT = FMT == FMT_TF32 ? 4 : 2;
+    static constexpr int NK = FMT == FMT_TF32 ? 8 : 4;            // MMAs along K = 64
+    static constexpr int ROW_BYTES = 64 * ELT + 16;               // padded row of the state tile (conflict-free stores)
+    static constexpr int BW = 16 * ELT / 4;                       // 32-bit words of B fragments per thread and n-tile
+};
+
+template <int FMT>
+__device__ __forceinline__ void mma_sync(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
+{
+    if (FMT == FMT_TF32)
+        asm volatile(
+            "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+            : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+            : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+    else if (FMT == FMT_BF16)
+        asm volatile(
+            "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+            : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+            : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+    else
+        asm volatile(
+            "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+            : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+            : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int FMT>
+__device__ __forceinline__ uint32_t pack2(float lo, float hi)
+{
+    if (FMT == FMT_BF16) return pack_bf16(lo, hi);
+    const __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+template <int FMT>
+__device__ __forceinline__ void store_state(uint8_t* row, int unit, float v)
+{
+    if (FMT == FMT_TF32) *reinterpret_cast<uint32_t*>(row + unit * 4) = to_tf32(v);
+    else if (FMT == FMT_BF16) *reinterpret_cast<__nv_bfloat16*>(row + unit * 2) = __float2bfloat16_rn(v);
+    else *reinterpret_cast<__half*>(row + unit * 2) = __float2half_rn(v);
+}
+
+template <int FMT, int NT>
+struct MmaCfg {
+    static constexpr int S = 8 * NT;                 // streams per CTA
+    static constexpr int CH = 32;                    // steps per staged chunk
+    static constexpr int YP_LD = S + 1;
+    static constexpr int HB_BYTES = S * Frag<FMT>::ROW_BYTES;
+    static constexpr int OFF_HB = 0;                               // [2][S][ROW_BYTES]
+    static constexpr int OFF_XS = (2 * HB_BYTES + 127) / 128 * 128;   // [2][CH][S] floats
+    static constexpr int OFF_YP = OFF_XS + 2 * CH * S * 4;         // [4 warps][CH][YP_LD] floats
+    static constexpr int SMEM_BYTES = OFF_YP + 4 * CH * YP_LD * 4;
+};
+
+template <int FMT, int NT>
+__global__ void __launch_bounds__(128, 2) gru_mma_kernel(const GruArgs a)
+{
+    using C = MmaCfg<FMT, NT>;
+    using F = Frag<FMT>;
+    constexpr int S = C::S, CH = C::CH, NK = F::NK, BW = F::BW;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* const hb = smem + C::OFF_HB;
+    float* const xs = reinterpret_cast<float*>(smem + C::OFF_XS);
+    float* const yp = reinterpret_cast<float*>(smem + C::OFF_YP);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int gid = lane >> 2, tig = lane & 3;
+    const int u0 = 16 * warp + gid, u1 = u0 + 8;
+    const long long b0 = (long long)blockIdx.x * S;
+    const int ns = (int)((a.B - b0) < (long long)S ? (a.B - b0) : (long long)S);
+    const float* __restrict__ blob = a.blob;
+
+    // ---- W_hh fragments -> registers -------------------------------------------------------------------------
+    // MMA k index (ks, kk) <-> actual hidden index is a free bijection as long as A and B agree: it is chosen so that
+    // a thread's B fragments of a whole step are plain vector loads from the state tile
+    //   f16/bf16: thread tig consumes elements tig*16 + 4ks + {0,1 | 2,3} in k-step ks
+    //   tf32:     thread tig consumes elements (ks/2)*16 + tig*4 + 2(ks%2) + {0 | 1}
+    uint32_t areg[3][NK][4];
+    {
+        const float sc_rz = -LOG2E_F, sc_n = 2.0f * LOG2E_F;
+        const float* wr0 = blob + BlobLayout::W_HH + (0 * 64 + u0) * 64;
+        const float* wz0 = blob + BlobLayout::W_HH + (1 * 64 + u0) * 64;
+        const float* wn0 = blob + BlobLayout::W_HH + (2 * 64 + u0) * 64;
+        const float* wr1 = wr0 + 8 * 64;
+        const float* wz1 = wz0 + 8 * 64;
+        const float* wn1 = wn0 + 8 * 64;
+        const float* lo[3] = {wr0, wr1, wn0};
+        const float* hi[3] = {wz0, wz1, wn1};
+        const float slo[3] = {sc_rz, sc_rz, sc_n}, shi[3] = {sc_rz, sc_rz, sc_n};
+#pragma unroll
+        for (int tile = 0; tile < 3; ++tile)
+#pragma unroll
+            for (int ks = 0; ks < NK; ++ks) {
+                if (FMT == FMT_TF32) {
+                    const int k = (ks >> 1) * 16 + tig * 4 + 2 * (ks & 1);
+                    areg[tile][ks][0] = to_tf32(slo[tile] * lo[tile][k]);
+                    areg[tile][ks][1] = to_tf32(shi[tile] * hi[tile][k]);
+                    areg[tile][ks][2] = to_tf32(slo[tile] * lo[tile][k + 1]);
+                    areg[tile][ks][3] = to_tf32(shi[tile] * hi[tile][k + 1]);
+                } else {
+                    const int k = tig * 16 + 4 * ks;
+                    areg[tile][ks][0] = pack2<FMT>(slo[tile] * lo[tile][k], slo[tile] * lo[tile][k + 1]);
+                    areg[tile][ks][1] = pack2<FMT>(shi[tile] * hi[tile][k], shi[tile] * hi[tile][k + 1]);
+                    areg[tile][ks][2] = pack2<FMT>(slo[tile] * lo[tile][k + 2], slo[tile] * lo[tile][k + 3]);
+                    areg[tile][ks][3] = pack2<FMT>(shi[tile] * hi[tile][k + 2], shi[tile] * hi[tile][k + 3]);
+                }
+            }
+    }
+    // per-unit constants (index 0: u0, 1: u1), scaled like the weights
+    float cr_w[2], cr_b[2], cz_w[2], cz_b[2], cn_w[2], cn_b[2], ch_b[2], wo[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int j = u ? u1 : u0;
+        cr_w[u] = -LOG2E_F * blob[BlobLayout::W_IH + j];
+        cr_b[u] = -LOG2E_F * (blob[BlobLayout::B_IH + j] + blob[BlobLayout::B_HH + j]);
+        cz_w[u] = -LOG2E_F * blob[BlobLayout::W_IH + 64 + j];
+        cz_b[u] = -LOG2E_F * (blob[BlobLayout::B_IH + 64 + j] + blob[BlobLayout::B_HH + 64 + j]);
+        cn_w[u] = 2.0f * LOG2E_F * blob[BlobLayout::W_IH + 128 + j];
+        cn_b[u] = 2.0f * LOG2E_F * blob[BlobLayout::B_IH + 128 + j];
+        ch_b[u] = 2.0f * LOG2E_F * blob[BlobLayout::B_HH + 128 + j];
+        wo[u] = blob[BlobLayout::W_OUT + j];
+    }
+    const float bo = blob[BlobLayout::B_OUT];
+
+    const bool delay = a.d != nullptr;
+    float* __restrict__ head_out = delay ? a.pre : a.y;
+    const long long ldo = delay ? a.ldp : a.ldy;
+
+    auto load_x = [&](int buf, long long t0) {
+        const int n = (int)((a.T - t0) < (long long)CH ? (a.T - t0) : (long long)CH);
+        float* dstb = xs + buf * CH * S;
+        for (int idx = tid; idx < CH * S; idx += 128) {
+            const int s = idx % S, tt = idx / S;
+            if (s < ns && tt < n) cp_async4(dstb + tt * S + s, a.x + (b0 + s) * a.ldx + t0 + tt);
+            else dstb[tt * S + s] = 0.0f;
+        }
+        cp_async_commit();
+    };
+
+    // ---- initial state: fp32 in registers (hst[nt][unit][stream]), rounded copy into state tile 0 ---------------
+    float hst[NT][2][2];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int s = nt * 8 + 2 * tig + e, j = u ? u1 : u0;
+                const float v = (s < ns && a.h_in) ? a.h_in[(b0 + s) * 64 + j] : 0.0f;
+                hst[nt][u][e] = v;
+                store_state<FMT>(hb + s * F::ROW_BYTES, j, v);
+            }
+    load_x(0, 0);
+
+    const long long nchunks = (a.T + CH - 1) / CH;
+    int cur = 0;
+    for (long long c = 0; c < nchunks; ++c) {
+        const long long t0 = c * CH;
+        const int n = (int)((a.T - t0) < (long long)CH ? (a.T - t0) : (long long)CH);
+        const int xb = (int)(c & 1);
+        const float* xcur = xs + xb * CH * S;
+        cp_async_wait_all();
+        __syncthreads();                       // xs[xb] landed; state tile `cur` complete; previous flush done
+        if (c + 1 < nchunks) load_x(xb ^ 1, t0 + CH);
+
+        for (int tt = 0; tt < n; ++tt) {
+            const uint8_t* hcur = hb + cur * C::HB_BYTES;
+            uint8_t* hnext = hb + (cur ^ 1) * C::HB_BYTES;
+            float acc[NT][3][4];
+            uint32_t breg[NT][BW];
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                // f16/bf16: the thread's 16 elements are contiguous (2 vectors); tf32: vector q holds elements
+                // q*16 + tig*4 .. +3 (4 vectors, quarter-warp reads 64 contiguous bytes)
+                const uint8_t* src = hcur + (nt * 8 + gid) * F::ROW_BYTES + (FMT == FMT_TF32 ? tig * 16 : tig * 32);
+#pragma unroll
+                for (int q = 0; q < BW / 4; ++q) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(src + q * (FMT == FMT_TF32 ? 64 : 16));
+                    breg[nt][4 * q] = v.x; breg[nt][4 * q + 1] = v.y; breg[nt][4 * q + 2] = v.z; breg[nt][4 * q + 3] = v.w;
+                }
+#pragma unroll
+                for (int tile = 0; tile < 3; ++tile) acc[nt][tile][0] = acc[nt][tile][1] = acc[nt][tile][2] = acc[nt][tile][3] = 0.0f;
+            }
+#pragma unroll
+            for (int ks = 0; ks < NK; ++ks)
+#pragma unroll
+                for (int tile = 0; tile < 3; ++tile)
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt)
+                        mma_sync<FMT>(acc[nt][tile], areg[tile][ks], breg[nt][2 * ks], breg[nt][2 * ks + 1]);
+
+            // ---- gates, state blend, rounded state for the next step, head partials ------------------------------
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                const float2 xv = *reinterpret_cast<const float2*>(xcur + tt * S + nt * 8 + 2 * tig);
+                float p[2] = {0.0f, 0.0f};
+#pragma unroll
+                for (int u = 0; u < 2; ++u)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const float x = e ? xv.y : xv.x;
+                        const float ar = acc[nt][u][e], az = acc[nt][u][2 + e], an = acc[nt][2][2 * u + e];
+                        const float er = ex2_approx(ar + fmaf(cr_w[u], x, cr_b[u]));
+                        const float ez = ex2_approx(az + fmaf(cz_w[u], x, cz_b[u]));
+                        const float r = rcp_approx(1.0f + er);
+                        const float z = rcp_approx(1.0f + ez);
+                        const float en = ex2_approx(fmaf(r, an + ch_b[u], fmaf(cn_w[u], x, cn_b[u])));
+                        const float nn = fmaf(-2.0f, rcp_approx(1.0f + en), 1.0f);
+                        const float hn = fmaf(z, hst[nt][u][e] - nn, nn);
+                        hst[nt][u][e] = hn;
+                        p[e] = fmaf(wo[u], hn, p[e]);
+                        store_state<FMT>(hnext + (nt * 8 + 2 * tig + e) * F::ROW_BYTES, u ? u1 : u0, hn);
+                    }
+                // head: sum over the warp's 16 units = over gid (lane bits 2..4)
+#pragma unroll
+                for (int m = 4; m <= 16; m <<= 1) {
+                    p[0] += __shfl_xor_sync(0xffffffffu, p[0], m);
+                    p[1] += __shfl_xor_sync(0xffffffffu, p[1], m);
+                }
+                if (gid == 0) {
+                    yp[(warp * CH + tt) * C::YP_LD + nt * 8 + 2 * tig] = p[0];
+                    yp[(warp * CH + tt) * C::YP_LD + nt * 8 + 2 * tig + 1] = p[1];
+                }
+            }
+            cur ^= 1;
+            __syncthreads();                   // next state tile published; all reads of the old one are done
+        }
+
+        // ---- flush the chunk: y = sum of the four warps' partials + bias (+ x) ------------------------------------
+        for (int idx = tid; idx < S * CH; idx += 128) {
+            const int s = idx / CH, tt = idx % CH;
+            if (s < ns && tt < n) {
+                float v = yp[tt * C::YP_LD + s] + yp[(CH + tt) * C::YP_LD + s] + yp[(2 * CH + tt) * C::YP_LD + s] +
+                          yp[(3 * CH + tt) * C::YP_LD + s] + bo;
+                if (a.skip) v += xcur[tt * S + s];
+                head_out[(b0 + s) * ldo + t0 + tt] = v;
+                if (delay && a.warmup) a.y[(b0 + s) * a.ldy + t0 + tt] = v;
+            }
+        }
+        if (delay && !a.warmup) {
+            __syncthreads();                   // this chunk's pre_d is visible CTA-wide (L2 reads below)
+            for (int idx = tid; idx < S * CH; idx += 128) {
+                const int s = idx / CH, tt = idx % CH;
+                if (s < ns && tt < n) {
+                    const long long tg = t0 + tt;
+                    const float* prow = a.pre + (b0 + s) * a.ldp;
+                    const float* hrow = a.hist_in + (b0 + s) * (long long)a.D;
+                    a.y[(b0 + s) * a.ldy + tg] =
+                        delay_read(a.d[(b0 + s) * a.ldd + tg], tg, a.D,
+                                   [&](long long i) { return i >= 0 ? __ldcg(prow + i) : hrow[a.D + i]; });
+                }
+            }
+        }
+    }
+
+    // ---- final state; rolled delay history (code/model.py:314-315) -------------------------------------------------
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int s = nt * 8 + 2 * tig + e;
+                if (s < ns) a.h_out[(b0 + s) * 64 + (u ? u1 : u0)] = hst[nt][u][e];
+            }
+    if (delay) {
+        __syncthreads();
+        for (long long idx = tid; idx < (long long)ns * a.D; idx += 128) {
+            const int s = (int)(idx / a.D);
+            const long long i = idx % a.D;
+            const long long src = a.T - a.D + i;
+            a.hist_out[(b0 + s) * (long long)a.D + i] =
+                src >= 0 ? __ldcg(a.pre + (b0 + s) * a.ldp + src) : a.hist_in[(b0 + s) * (long long)a.D + a.D + src];
+        }
+    }
+}
+
+template <int FMT, int NT>
+cudaError_t launch_mma_one(const GruArgs& a, cudaStream_t st)
+{
+    using C = MmaCfg<FMT, NT>;
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 64 && !configured[dev]) {
+        e = cudaFuncSetAttribute(gru_mma_kernel<FMT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        configured[dev] = true;
+    }
+    const long long grid = (a.B + C::S - 1) / C::S;
+    gru_mma_kernel<FMT, NT><<<(unsigned)grid, 128, C::SMEM_BYTES, st>>>(a);
+    ++g_launches;
+    return cudaGetLastError();
+}
+
+template <int FMT>
+cudaError_t launch_mma_fmt(const GruArgs& a, int nt, cudaStream_t st)
+{
+    if (nt >= 2) return launch_mma_one<FMT, 2>(a, st);
+    return launch_mma_one<FMT, 1>(a, st);
+}
+
+}  // namespace
+
+// fmt: FMT_F16 / FMT_BF16 / FMT_TF32.  n_tiles: 8-stream tiles per CTA (1 or 2).
+cudaError_t launch_gru_mma(const GruArgs& a, int fmt, int n_tiles, cudaStream_t st)
+{
+    if (a.B <= 0 || a.T <= 0) return cudaSuccess;
+    switch (fmt) {
+        case FMT_TF32: return launch_mma_fmt<FMT_TF32>(a, n_tiles, st);
+        case FMT_BF16: return launch_mma_fmt<FMT_BF16>(a, n_tiles, st);
+        default: return launch_mma_fmt<FMT_F16>(a, n_tiles, st);
+    }
+}
+
+}  // namespace ntm

@@ -298,7 +298,10 @@ def test_cfg2_width_properties():
     with torch.inference_mode():
         y = m.predict(x)
         halves = torch.cat([m.predict(x[:512]), m.predict(x[512:])], 0)
-        assert torch.equal(halves, y)
+        assert float((halves - y).abs().max()) < 3e-6      # the dispatcher may pick another k-split for 512 streams
+        lib.load().ntm_set_tuning(4, 4)
+        assert torch.equal(torch.cat([m.predict(x[:512]), m.predict(x[512:])], 0), m.predict(x))
+        lib.load().ntm_set_tuning(0, 0)
         pick = [0, 1, 2, 3, 509, 1022, 1023]
         yr, _ = ref_torch.RefNet(load_ckpt("cfg2")).predict(x[pick].cpu())
         assert float((y[pick].cpu() - yr).abs().max()) <= TOL

@@ -1,0 +1,183 @@
+"""Tensor-core modes (tcgen05 kernel, csrc/gru_tc.cu) through the C ABI.
+
+Tolerance (BASELINE.json north_star): tf32/bf16-class MMA modes -- ESR of the output against the reference's fp32
+output <= 1e-4 on numerically stable inputs.  "f16" rounds the operands to an 11-bit significand exactly like tf32 and
+is held to the same bound; "bf16" (8-bit significand) is the opt-in low-accuracy mode and is only required to stay
+finite and roughly right (SURVEY.md H2 measured ESR 1e-3..1e-2 for it).
+Where a checkpoint amplifies round-off on a signal (reference fp32-vs-fp64 floor >= 5e-6: the cfg-1 pulse train) or the
+target is (near) silence -- ESR of a ~1e-3 DC level -- the bound is on max-abs instead.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import SIGNALS, load_ckpt, load_golden
+from ntm_b200 import DiffDelRNN, RNN, lib, signals
+from oracle import c_oracle, ref_torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+ESR_TOL = 1e-4
+TC_MODES = ("f16", "tf32")
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def make_rnn(tag, mode, skip=False):
+    m = RNN(input_size=1, hidden_size=64, output_size=1, skip=skip).to(DEV)
+    m.load_state_dict(load_ckpt(tag))
+    m.mode = mode
+    return m
+
+
+@pytest.fixture(autouse=True)
+def _auto_tuning():
+    lib.load().ntm_set_tuning(0, 0)
+    yield
+    lib.load().ntm_set_tuning(0, 0)
+
+
+def test_mode_mask():
+    mask = lib.query(lib.Q_MODE_MASK)
+    for m in ("fp32", "tf32", "bf16", "f16"):
+        assert mask >> lib.MODES[m] & 1
+    assert not mask >> lib.MODES["tf32x3"] & 1
+    m = make_rnn("cfg1", "tf32x3")
+    with pytest.raises(RuntimeError, match="unsupported"):
+        m.predict(torch.zeros(1, 1, 64, device=DEV))
+
+
+@pytest.mark.parametrize("kernel", [(8, 1), (8, 3)])
+@pytest.mark.parametrize("mode", TC_MODES)
+@pytest.mark.parametrize("tag", ["cfg1", "cfg2"])
+def test_tc_predict_esr_vs_golden(tag, mode, kernel):
+    lib.load().ntm_set_tuning(*kernel)
+    m = make_rnn(tag, mode)
+    g = load_golden(f"golden_{tag}")
+    with torch.inference_mode():
+        for sig in SIGNALS:
+            y = m.predict(dev(g[f"x_{sig}"]).reshape(1, 1, -1)).cpu().numpy().reshape(-1)
+            ref = g[f"y_{sig}"]
+            stable = float(g[f"floor_{sig}"]) < 5e-6 and sig != "silence"
+            if stable:
+                assert c_oracle.esr(y, ref) <= ESR_TOL, (tag, mode, sig, c_oracle.esr(y, ref))
+                assert np.max(np.abs(y - ref)) <= 5e-3, (tag, mode, sig)
+            else:
+                assert np.all(np.isfinite(y)) and np.max(np.abs(y - ref)) <= 5e-2, (tag, mode, sig)
+
+
+def test_bf16_is_finite_and_close():
+    m = make_rnn("cfg2", "bf16")
+    g = load_golden("golden_cfg2")
+    with torch.inference_mode():
+        y = m.predict(dev(g["x_sweepnoise_lo"]).reshape(1, 1, -1)).cpu().numpy().reshape(-1)
+    assert np.all(np.isfinite(y)) and c_oracle.esr(y, g["y_sweepnoise_lo"]) <= 5e-2
+
+
+@pytest.mark.parametrize("mode", TC_MODES)
+def test_tc_batch_vs_oracle_and_launch_shapes(mode):
+    """64 mixed streams x 0.25 s against the torch restatement of the reference; every (streams per group,
+    groups per CTA) variant of the kernel and a ragged batch give the same answer per stream."""
+    m = make_rnn("cfg2", mode)
+    B, T = 77, 12000
+    xh = signals.stream_batch(B, T, dur=10.0)
+    x = dev(xh).reshape(B, 1, T)
+    yr, _ = ref_torch.RefNet(load_ckpt("cfg2")).predict(torch.from_numpy(xh).reshape(B, 1, T))
+    with torch.inference_mode():
+        y0 = m.predict(x)
+        per_stream = ((y0.cpu() - yr) ** 2).sum(2) / ((yr ** 2).sum(2) + 1e-5)
+        assert float(per_stream.max()) <= ESR_TOL
+        assert abs(c_oracle.esr(y0.cpu().numpy(), yr.numpy())) <= ESR_TOL
+        # g = 1, 2: tcgen05 kernel with n streams per group; g = 3: warp-level mma.sync kernel with n streams per CTA
+        fam = {}
+        for n, g in ((8, 1), (16, 1), (32, 1), (64, 1), (8, 2), (16, 2), (32, 2), (64, 2), (8, 3), (16, 3)):
+            lib.load().ntm_set_tuning(n, g)
+            y = m.predict(x)
+            per_stream = ((y.cpu() - yr) ** 2).sum(2) / ((yr ** 2).sum(2) + 1e-5)
+            assert float(per_stream.max()) <= ESR_TOL, (n, g)
+            first = fam.setdefault(g == 3, y)
+            assert float((y - first).abs().max()) <= 1e-6, (n, g)      # same kernel family: same arithmetic
+            for b in (0, 31, 76):
+                assert float((m.predict(x[b:b + 1]) - y[b:b + 1]).abs().max()) <= 1e-6
+
+
+@pytest.mark.parametrize("kernel", [(0, 0), (8, 1), (8, 3)])
+@pytest.mark.parametrize("mode", TC_MODES)
+def test_tc_segmentation_state_and_skip(mode, kernel):
+    lib.load().ntm_set_tuning(*kernel)
+    m = make_rnn("cfg1", mode)
+    B, T = 5, 3000
+    x = dev(signals.stream_batch(B, T)).reshape(B, 1, T)
+    with torch.inference_mode():
+        y_all = m.predict(x)
+        h_all = m.hidden.clone()
+        m.predict(x[:, :, :0])
+        parts, s = [], 0
+        for n in (64, 1, 31, 32, 33, 2000, 839):
+            parts.append(m(x[:, :, s:s + n]))
+            s += n
+        assert s == T
+        assert torch.equal(torch.cat(parts, 2), y_all) and torch.equal(m.hidden, h_all)
+        ms = make_rnn("cfg1", mode, skip=True)
+        assert torch.allclose(ms.predict(x), y_all + x, atol=1e-7, rtol=0)
+        view = x[:, :, 7:1507]                               # unaligned, strided rows
+        assert torch.equal(m.predict(view), m.predict(view.contiguous()))
+
+
+@pytest.mark.parametrize("kernel", [(16, 2), (8, 3)])
+@pytest.mark.parametrize("mode", TC_MODES)
+def test_tc_diffdel(mode, kernel):
+    lib.load().ntm_set_tuning(*kernel)
+    g = load_golden("golden_cfg3")
+    D = int(g["max_delay"])
+    m = DiffDelRNN(input_size=1, hidden_size=64, output_size=1, skip=False, max_delay=D).to(DEV)
+    m.load_state_dict(load_ckpt("cfg3"))
+    m.mode = mode
+    with torch.inference_mode():
+        for sig in ("sweepnoise", "noise", "sine"):
+            x, d = dev(g[f"x_{sig}"]).reshape(1, 1, -1), dev(g[f"d_{sig}"]).reshape(1, 1, -1)
+            y, pre = m.predict(x, d)
+            y, pre = y.cpu().numpy().reshape(-1), pre.cpu().numpy().reshape(-1)
+            assert c_oracle.esr(pre, g[f"pre_{sig}"]) <= ESR_TOL, (sig, c_oracle.esr(pre, g[f"pre_{sig}"]))
+            assert c_oracle.esr(y, g[f"y_{sig}"]) <= ESR_TOL, (sig, c_oracle.esr(y, g[f"y_{sig}"]))
+            # the fused delay read is bit-exact given the engine's own pre_d and warm history
+            m.initialize_hidden(1, m.max_delay)
+            m.warm_start()
+            hist_w = m.diffdel.buffer.cpu().numpy().reshape(1, -1)
+            yo, _ = c_oracle.delay_forward(pre.reshape(1, -1), g[f"d_{sig}"].reshape(1, -1), hist_w)
+            assert np.array_equal(yo.reshape(-1), y), sig
+        # batch + ragged segments with carried state and history
+        B, T = 19, 4000
+        x = dev(signals.stream_batch(B, T)).reshape(B, 1, T)
+        d = dev(signals.delay_trajectory(B, T)).reshape(B, 1, T)
+        y_all, p_all = m.predict(x, d)
+        hist_all = m.diffdel.buffer.clone()
+        m.predict(x[:, :, :0], d[:, :, :0])
+        ys, ps, s = [], [], 0
+        for n in (2048, 100, 1, 365, 1486):
+            yy, pp = m(x[:, :, s:s + n], d[:, :, s:s + n])
+            ys.append(yy)
+            ps.append(pp)
+            s += n
+        assert s == T
+        assert torch.equal(torch.cat(ps, 2), p_all) and torch.equal(torch.cat(ys, 2), y_all)
+        assert torch.equal(m.diffdel.buffer, hist_all)
+
+
+def test_tc_cfg2_width_and_host_pipeline():
+    """1024 streams (cfg 2 width): sampled streams against the host oracle, split-batch checksum, host pipeline."""
+    m = make_rnn("cfg2", "f16")
+    B, T = 1024, 6000
+    x = signals.stream_batch_device(B, T, DEV, dur=10.0).reshape(B, 1, T)
+    with torch.inference_mode():
+        y = m.predict(x)
+        halves = torch.cat([m.predict(x[:512]), m.predict(x[512:])], 0)
+        assert float((halves - y).abs().max()) <= 1e-6
+        pick = [0, 1, 2, 3, 509, 1022, 1023]
+        yr, _ = ref_torch.RefNet(load_ckpt("cfg2")).predict(x[pick].cpu())
+        per_stream = ((y[pick].cpu() - yr) ** 2).sum(2) / ((yr ** 2).sum(2) + 1e-5)
+        assert float(per_stream.max()) <= ESR_TOL
+        xh = x[:16].cpu().pin_memory()
+        assert torch.equal(m.predict_host(xh, chunk=2048), m.predict(x[:16]).cpu())
