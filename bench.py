@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Headline benchmark: GRU-HS[64] samples/s (BASELINE.json metric), one JSON line on stdout.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mode fp32|tf32|bf16|tf32x3]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mode f16|tf32|bf16|fp32]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
            bench.py --gpus N --steps K --warmup W
 
@@ -150,7 +150,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default="fp32", choices=["fp32", "tf32", "bf16", "tf32x3"])
+    ap.add_argument("--mode", default="f16", choices=["fp32", "f16", "tf32", "bf16"])
     ap.add_argument("--streams", type=int, default=1024)
     ap.add_argument("--seconds", type=float, default=60.0)
     ap.add_argument("--e2e-steps", type=int, default=2)
@@ -167,7 +167,7 @@ def main():
         return
 
     import ntm_b200
-    from ntm_b200 import lib, signals
+    from ntm_b200 import lib, sharding, signals
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: ntm_b200 has no CPU path")
     torch.cuda.set_device(local_rank)
@@ -181,7 +181,8 @@ def main():
     model = ntm_b200.RNN(input_size=1, hidden_size=64, output_size=1, skip=False).to(dev)
     model.load_state_dict(load_sd("cfg2"))
     model.mode = args.mode
-    x = signals.stream_batch_device(B, T, dev, first_stream=rank * B, dur=args.seconds).reshape(B, 1, T)
+    first, _ = sharding.weak_scaling_range(B, rank)         # this rank's own streams; nothing is exchanged
+    x = signals.stream_batch_device(B, T, dev, first_stream=first, dur=args.seconds).reshape(B, 1, T)
     torch.cuda.synchronize(dev)
 
     def barrier():
@@ -211,34 +212,30 @@ def main():
             ev[1].record()
             barrier()
         launches = L.ntm_query(lib.Q_KERNEL_LAUNCHES) - launches0
+        kernel_name = lib.KERNEL_NAMES.get(L.ntm_query(lib.Q_LAST_KERNEL), "?")
         total_ms = ev[0].elapsed_time(ev[1])
         kern_ms = sum(ev[2 + 2 * i].elapsed_time(ev[3 + 2 * i]) for i in range(args.steps)) / args.steps
         checksum = float(y[:, :, ::4801].double().sum())
         del y
-        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-        if dist is not None:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
-        value = world * B * T * args.steps / (total_ms * 1e-3)
+        total_ms = sharding.max_over_ranks(total_ms, dev, dist)
+        value = sharding.aggregate_rate(B * T * args.steps, world, total_ms * 1e-3)
 
         # ---- end to end: pinned host in -> engine pipeline -> pinned host out -------------------------
         import psutil
         avail = psutil.virtual_memory().available
-        need = 2 * B * T * 4 * max(1, min(world, 8))
+        need = 2 * B * T * 4 * max(1, min(world, 8))          # pinned x and y of every rank on this host
         T_e = T if need < 0.5 * avail else max(FS, int(0.25 * avail / (8 * B * max(1, world))) // FS * FS)
         xh = torch.empty((B, 1, T_e), dtype=torch.float32, pin_memory=True)
         xh.copy_(x[:, :, :T_e])
-        model.predict_host(xh)
+        yh = torch.empty((B, 1, T_e), dtype=torch.float32, pin_memory=True)      # result buffer reused across steps
+        model.predict_host(xh, out=yh)
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
-            yh = model.predict_host(xh)
+            model.predict_host(xh, out=yh)
         torch.cuda.synchronize(dev)
         e2e_s = time.perf_counter() - t0
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        if dist is not None:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_value = world * B * T_e * args.e2e_steps / float(t.item())
+        e2e_value = sharding.aggregate_rate(B * T_e * args.e2e_steps, world, sharding.max_over_ranks(e2e_s, dev, dist))
         e2e_ok = bool(torch.isfinite(yh[:, :, ::4801]).all())
         del xh, yh
 
@@ -261,7 +258,9 @@ def main():
     line = {
         "metric": "GRU-HS64 samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32", "bf16": "bf16", "tf32x3": "tf32x3"}[args.mode],
+        "vs_baseline": None,
+        "dtype": {"fp32": "f32", "f16": "f16 operands, f32 accumulate/gates/state", "tf32": "tf32 operands, f32 accumulate/gates/state",
+                  "bf16": "bf16 operands, f32 accumulate/gates/state"}[args.mode],
         "data": "synthetic",
         "config": {"workload": WORKLOAD.format(B=B, sec=args.seconds), "streams_per_gpu": B, "samples_per_stream": T,
                    "sample_rate": FS, "mode": args.mode, "parallelism": f"stream-sharded x{world}, no collective",
@@ -275,7 +274,11 @@ def main():
         "roofline": {
             "bound": "tensor", "achieved": achieved_tflops, "peak": tensor_peak, "unit": "TFLOP/s",
             "frac": achieved_tflops / tensor_peak, "traffic": None, "peak_source": peak_src,
-            "kernel_ms": kern_ms, "kernel": "gru_fp32_kernel" if args.mode == "fp32" else f"gru_{args.mode}",
+            "kernel_ms": kern_ms, "kernel": kernel_name,
+            "regime": "latency-bound recurrence: 1024 streams = 7 per SM, one dependent GRU step at a time (DESIGN.md section 4)",
+            "legacy_mma_sync_peak_tflops": sm_count * 4 * 4096 / 8 * f_clk / 1e12,
+            "frac_of_mma_sync_peak": achieved_tflops / (sm_count * 4 * 4096 / 8 * f_clk / 1e12),
+            "ns_per_timestep": kern_ms * 1e6 / T,
             "fp32_fma_peak_tflops": sm_count * 128 * 2 * f_clk / 1e12,
             "frac_of_fp32_fma_peak": achieved_tflops / (sm_count * 128 * 2 * f_clk / 1e12),
             "mufu_bound_samples_per_s": sm_count * 16 * f_clk / 192,
@@ -314,15 +317,40 @@ def aux_measurements(ntm_b200, signals, dev, mode):
         m1(x1[:, :, 64 * k:64 * k + 64])
     torch.cuda.synchronize(dev)
     out["batch1_block64_ns_per_sample_incl_launch"] = (time.perf_counter() - t0) * 1e9 / (nblk * 64)
+    from ntm_b200 import lib
+    L = lib.load()
     mb = ntm_b200.RNN(1, 64, 1, False).to(dev)
     mb.load_state_dict(load_sd("cfg2"))
-    mb.mode = mode
-    Bb, Tb = 16384, 24000
-    xb = signals.stream_batch_device(Bb, Tb, dev, dur=10.0).reshape(Bb, 1, Tb)
-    mb.predict(xb[:, :, :2400])
-    mb.initialize_hidden(); mb.warm_start(); mb.hidden = mb.hidden.expand(1, Bb, 64).contiguous()
-    e0.record(); mb(xb); e1.record(); torch.cuda.synchronize(dev)
-    out["large_batch"] = {"streams": Bb, "samples_per_stream": Tb, "samples_per_s": Bb * Tb / (e0.elapsed_time(e1) * 1e-3)}
+
+    def timed(x, m, tuning=(0, 0)):
+        B = x.shape[0]
+        L.ntm_set_tuning(*tuning)
+        m.predict(x[:, :, :1200])
+        m.initialize_hidden(); m.warm_start(); m.hidden = m.hidden.expand(1, B, 64).contiguous()
+        e0.record(); m(x); e1.record(); torch.cuda.synchronize(dev)
+        L.ntm_set_tuning(0, 0)
+        return B * x.shape[2] / (e0.elapsed_time(e1) * 1e-3)
+
+    # the same 1024-stream workload (2 s of it) in every arithmetic mode, and the tcgen05 kernel forced
+    x2 = signals.stream_batch_device(1024, 96000, dev, dur=60.0).reshape(1024, 1, 96000)
+    per_mode = {}
+    for md in ("fp32", "f16", "tf32", "bf16"):
+        mb.mode = md
+        per_mode[md] = timed(x2, mb)
+    mb.mode = "f16"
+    per_mode["f16_tcgen05_kernel"] = timed(x2, mb, (8, 1))
+    out["cfg2_samples_per_s_by_mode"] = per_mode
+    del x2
+    # throughput regime (cfg 4 per-GPU widths): both tensor-core kernels
+    big = {}
+    for Bb, Tb in ((8192, 12000), (65536, 3000)):
+        xb = signals.stream_batch_device(Bb, Tb, dev, dur=10.0).reshape(Bb, 1, Tb)
+        mb.mode = "f16"
+        big[str(Bb)] = {"mma_sync": timed(xb, mb, (8, 3)), "tcgen05": timed(xb, mb, (64, 2))}
+        mb.mode = "fp32"
+        big[str(Bb)]["fp32_cuda_core"] = timed(xb, mb)
+        del xb
+    out["large_batch_samples_per_s"] = big
     return out
 
 

@@ -54,6 +54,7 @@ extern "C" {
 #define NTM_Q_SM_COUNT       2   /* of the current device */
 #define NTM_Q_MODE_MASK      3   /* bit m set <=> mode m is implemented */
 #define NTM_Q_KERNEL_LAUNCHES 4  /* number of engine kernels launched by this process so far */
+#define NTM_Q_LAST_KERNEL    5   /* recurrent kernel of the last launch: 0 fp32 CUDA-core, 1 mma.sync, 2 tcgen05 */
 
 int         ntm_query(int what);
 const char* ntm_strerror(int code);

@@ -15,6 +15,7 @@ namespace {
 constexpr unsigned HANDLE_MAGIC = 0x4e544d42u;   // "NTMB"
 thread_local int t_last_cuda = 0;
 int g_tune_s = 0, g_tune_ks = 0, g_tune_fast = 0;
+int g_last_kernel = -1;             // 0 fp32 CUDA-core, 1 warp-level mma.sync, 2 tcgen05 (ntm_query NTM_Q_LAST_KERNEL)
 long long g_mma_streams_per_sm = 1ll << 40;   // crossover between the two tensor-core kernels (measured)
 
 struct HostPipe {            // staging of the *_host entry points
@@ -70,6 +71,7 @@ int run_gru(Handle* hd, int mode, const ntm::GruArgs& a, cudaStream_t st)
     if (!mode_supported(mode)) return NTM_EUNSUPPORTED;
     if (mode == NTM_MODE_FP32) {
         CU(ntm::launch_gru_fp32(a, hd->sm_count, g_tune_s, g_tune_ks & 0xff, g_tune_fast, st));
+        g_last_kernel = 0;
     } else {
         const int fmt = mode == NTM_MODE_TF32 ? 2 : mode == NTM_MODE_BF16 ? 1 : 0;    // tc_prims.cuh FMT_*
         // latency regime (few streams per SM): warp-level mma.sync kernel; throughput regime: tcgen05 kernel.
@@ -79,8 +81,10 @@ int run_gru(Handle* hd, int mode, const ntm::GruArgs& a, cudaStream_t st)
         if (use_mma) {
             const int nt = g_tune_s > 0 && tg == 3 ? g_tune_s / 8 : 1;
             CU(ntm::launch_gru_mma(a, fmt, nt, st));
+            g_last_kernel = 1;
         } else {
             CU(ntm::launch_gru_tc(a, fmt, hd->sm_count, tg ? g_tune_s : 0, tg, st));
+            g_last_kernel = 2;
         }
     }
     return NTM_OK;
@@ -219,6 +223,7 @@ int ntm_query(int what)
         }
         case NTM_Q_MODE_MASK: return MODE_MASK;
         case NTM_Q_KERNEL_LAUNCHES: return (int)(ntm::g_launches & 0x7fffffffull);
+        case NTM_Q_LAST_KERNEL: return g_last_kernel;
         default: return NTM_EINVAL;
     }
 }

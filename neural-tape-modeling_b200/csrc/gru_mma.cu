@@ -20,7 +20,7 @@
 // for the whole kernel (pre-scaled by -log2 e / 2 log2 e, rounded once to the operand format).  The rounded state
 // lives in a double-buffered shared-memory tile laid out so that each thread fetches all its B fragments of a step
 // with two (f16/bf16) or four (tf32) LDS.128; the fp32 state never leaves registers.  One __syncthreads per step.
-#include "ntm_common.cuh"
+#include "gates.cuh"
 #include "tc_prims.cuh"
 
 namespace ntm {
@@ -67,19 +67,19 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi)
     return *reinterpret_cast<const uint32_t*>(&h);
 }
 
+// rounded states of the adjacent units (unit, unit + 1) of one stream; unit is even
 template <int FMT>
-__device__ __forceinline__ void store_state(uint8_t* row, int unit, float v)
+__device__ __forceinline__ void store_state2(uint8_t* row, int unit, float v0, float v1)
 {
-    if (FMT == FMT_TF32) *reinterpret_cast<uint32_t*>(row + unit * 4) = to_tf32(v);
-    else if (FMT == FMT_BF16) *reinterpret_cast<__nv_bfloat16*>(row + unit * 2) = __float2bfloat16_rn(v);
-    else *reinterpret_cast<__half*>(row + unit * 2) = __float2half_rn(v);
+    if (FMT == FMT_TF32) *reinterpret_cast<uint2*>(row + unit * 4) = make_uint2(to_tf32(v0), to_tf32(v1));
+    else *reinterpret_cast<uint32_t*>(row + unit * 2) = pack2<FMT>(v0, v1);
 }
 
 template <int FMT, int NT>
 struct MmaCfg {
     static constexpr int S = 8 * NT;                 // streams per CTA
     static constexpr int CH = 32;                    // steps per staged chunk
-    static constexpr int YP_LD = S + 1;
+    static constexpr int YP_LD = S + 2;              // even: float2 stores of the head partials
     static constexpr int HB_BYTES = S * Frag<FMT>::ROW_BYTES;
     static constexpr int OFF_HB = 0;                               // [2][S][ROW_BYTES]
     static constexpr int OFF_XS = (2 * HB_BYTES + 127) / 128 * 128;   // [2][CH][S] floats
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(128, 2) gru_mma_kernel(const GruArgs a)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int gid = lane >> 2, tig = lane & 3;
-    const int u0 = 16 * warp + gid, u1 = u0 + 8;
+    const int u0 = 16 * warp + 2 * gid, u1 = u0 + 1;      // adjacent units: their rounded states share a store
     const long long b0 = (long long)blockIdx.x * S;
     const int ns = (int)((a.B - b0) < (long long)S ? (a.B - b0) : (long long)S);
     const float* __restrict__ blob = a.blob;
@@ -116,9 +116,9 @@ __global__ void __launch_bounds__(128, 2) gru_mma_kernel(const GruArgs a)
         const float* wr0 = blob + BlobLayout::W_HH + (0 * 64 + u0) * 64;
         const float* wz0 = blob + BlobLayout::W_HH + (1 * 64 + u0) * 64;
         const float* wn0 = blob + BlobLayout::W_HH + (2 * 64 + u0) * 64;
-        const float* wr1 = wr0 + 8 * 64;
-        const float* wz1 = wz0 + 8 * 64;
-        const float* wn1 = wn0 + 8 * 64;
+        const float* wr1 = wr0 + 64;
+        const float* wz1 = wz0 + 64;
+        const float* wn1 = wn0 + 64;
         const float* lo[3] = {wr0, wr1, wn0};
         const float* hi[3] = {wz0, wz1, wn1};
         const float slo[3] = {sc_rz, sc_rz, sc_n}, shi[3] = {sc_rz, sc_rz, sc_n};
@@ -142,20 +142,61 @@ __global__ void __launch_bounds__(128, 2) gru_mma_kernel(const GruArgs a)
             }
     }
     // per-unit constants (index 0: u0, 1: u1), scaled like the weights
-    float cr_w[2], cr_b[2], cz_w[2], cz_b[2], cn_w[2], cn_b[2], ch_b[2], wo[2];
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-        const int j = u ? u1 : u0;
-        cr_w[u] = -LOG2E_F * blob[BlobLayout::W_IH + j];
-        cr_b[u] = -LOG2E_F * (blob[BlobLayout::B_IH + j] + blob[BlobLayout::B_HH + j]);
-        cz_w[u] = -LOG2E_F * blob[BlobLayout::W_IH + 64 + j];
-        cz_b[u] = -LOG2E_F * (blob[BlobLayout::B_IH + 64 + j] + blob[BlobLayout::B_HH + 64 + j]);
-        cn_w[u] = 2.0f * LOG2E_F * blob[BlobLayout::W_IH + 128 + j];
-        cn_b[u] = 2.0f * LOG2E_F * blob[BlobLayout::B_IH + 128 + j];
-        ch_b[u] = 2.0f * LOG2E_F * blob[BlobLayout::B_HH + 128 + j];
-        wo[u] = blob[BlobLayout::W_OUT + j];
-    }
+    const UnitConst uc[2] = {load_unit_const(blob, u0), load_unit_const(blob, u1)};
     const float bo = blob[BlobLayout::B_OUT];
+    // Output head on the tensor core: an extra m16 tile whose row 0 is w_out rounded to the operand format and whose
+    // row 8 is the rounding residual (so w_out enters with ~2x the operand precision); the other rows are zero.  It is
+    // contracted with the SAME B fragments, i.e. with the rounded state of the previous step, K split over the four
+    // warps (warp w takes k-steps w*NK/4 ..), and lands in c0..c3 of the lanes gid == 0: y(2tig) = c0 + c2, y(2tig+1) =
+    // c1 + c3.  The four warps' partial sums are added at the chunk flush.
+    constexpr int HK = NK / 4;
+    uint32_t ahead[HK][4];
+#pragma unroll
+    for (int q = 0; q < HK; ++q) {
+        const int ks = warp * HK + q;
+        float w[4], hi[4], lo[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int k = FMT == FMT_TF32 ? (ks >> 1) * 16 + tig * 4 + 2 * (ks & 1) + (i & 1) : tig * 16 + 4 * ks + i;
+            w[i] = (gid == 0 && (FMT != FMT_TF32 || i < 2)) ? blob[BlobLayout::W_OUT + k] : 0.0f;
+            if (FMT == FMT_TF32) hi[i] = __uint_as_float(to_tf32(w[i]));
+            else if (FMT == FMT_BF16) hi[i] = __bfloat162float(__float2bfloat16_rn(w[i]));
+            else hi[i] = __half2float(__float2half_rn(w[i]));
+            lo[i] = w[i] - hi[i];
+        }
+        if (FMT == FMT_TF32) {      // a0 (row 0, k) a1 (row 8, k) a2 (row 0, k+1) a3 (row 8, k+1)
+            ahead[q][0] = to_tf32(hi[0]); ahead[q][1] = to_tf32(lo[0]); ahead[q][2] = to_tf32(hi[1]); ahead[q][3] = to_tf32(lo[1]);
+        } else {                    // a0 (row 0, k..k+1) a1 (row 8, k..k+1) a2 (row 0, k+2..k+3) a3 (row 8, k+2..k+3)
+            ahead[q][0] = pack2<FMT>(hi[0], hi[1]); ahead[q][1] = pack2<FMT>(lo[0], lo[1]);
+            ahead[q][2] = pack2<FMT>(hi[2], hi[3]); ahead[q][3] = pack2<FMT>(lo[2], lo[3]);
+        }
+    }
+    // this warp's k-steps of the B fragments (warp-uniform selects; a dynamic index would spill the array)
+    auto head_mma = [&](const uint32_t (&b)[BW], float (&c)[4]) {
+        c[0] = c[1] = c[2] = c[3] = 0.0f;
+#pragma unroll
+        for (int q = 0; q < HK; ++q) {
+            uint32_t b0, b1;
+            if (HK == 1) {
+                b0 = (warp & 2) ? ((warp & 1) ? b[6] : b[4]) : ((warp & 1) ? b[2] : b[0]);
+                b1 = (warp & 2) ? ((warp & 1) ? b[7] : b[5]) : ((warp & 1) ? b[3] : b[1]);
+            } else {
+                b0 = (warp & 2) ? ((warp & 1) ? b[12 + 2 * q] : b[8 + 2 * q]) : ((warp & 1) ? b[4 + 2 * q] : b[2 * q]);
+                b1 = (warp & 2) ? ((warp & 1) ? b[13 + 2 * q] : b[9 + 2 * q]) : ((warp & 1) ? b[5 + 2 * q] : b[1 + 2 * q]);
+            }
+            mma_sync<FMT>(c, ahead[q], b0, b1);
+        }
+    };
+    auto load_bfrag = [&](const uint8_t* tile, int nt, uint32_t (&b)[BW]) {
+        // f16/bf16: the thread's 16 elements are contiguous (2 vectors); tf32: vector q holds elements
+        // q*16 + tig*4 .. +3 (4 vectors, a quarter-warp reads 64 contiguous bytes)
+        const uint8_t* src = tile + (nt * 8 + gid) * F::ROW_BYTES + (FMT == FMT_TF32 ? tig * 16 : tig * 32);
+#pragma unroll
+        for (int q = 0; q < BW / 4; ++q) {
+            const uint4 v = *reinterpret_cast<const uint4*>(src + q * (FMT == FMT_TF32 ? 64 : 16));
+            b[4 * q] = v.x; b[4 * q + 1] = v.y; b[4 * q + 2] = v.z; b[4 * q + 3] = v.w;
+        }
+    };
 
     const bool delay = a.d != nullptr;
     float* __restrict__ head_out = delay ? a.pre : a.y;
@@ -177,14 +218,12 @@ __global__ void __launch_bounds__(128, 2) gru_mma_kernel(const GruArgs a)
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-        for (int u = 0; u < 2; ++u)
+        for (int e = 0; e < 2; ++e) {
+            const int s = nt * 8 + 2 * tig + e;
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int s = nt * 8 + 2 * tig + e, j = u ? u1 : u0;
-                const float v = (s < ns && a.h_in) ? a.h_in[(b0 + s) * 64 + j] : 0.0f;
-                hst[nt][u][e] = v;
-                store_state<FMT>(hb + s * F::ROW_BYTES, j, v);
-            }
+            for (int u = 0; u < 2; ++u) hst[nt][u][e] = (s < ns && a.h_in) ? a.h_in[(b0 + s) * 64 + u0 + u] : 0.0f;
+            store_state2<FMT>(hb + s * F::ROW_BYTES, u0, hst[nt][0][e], hst[nt][1][e]);
+        }
     load_x(0, 0);
 
     const long long nchunks = (a.T + CH - 1) / CH;
@@ -205,14 +244,7 @@ __global__ void __launch_bounds__(128, 2) gru_mma_kernel(const GruArgs a)
             uint32_t breg[NT][BW];
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) {
-                // f16/bf16: the thread's 16 elements are contiguous (2 vectors); tf32: vector q holds elements
-                // q*16 + tig*4 .. +3 (4 vectors, quarter-warp reads 64 contiguous bytes)
-                const uint8_t* src = hcur + (nt * 8 + gid) * F::ROW_BYTES + (FMT == FMT_TF32 ? tig * 16 : tig * 32);
-#pragma unroll
-                for (int q = 0; q < BW / 4; ++q) {
-                    const uint4 v = *reinterpret_cast<const uint4*>(src + q * (FMT == FMT_TF32 ? 64 : 16));
-                    breg[nt][4 * q] = v.x; breg[nt][4 * q + 1] = v.y; breg[nt][4 * q + 2] = v.z; breg[nt][4 * q + 3] = v.w;
-                }
+                load_bfrag(hcur, nt, breg[nt]);
 #pragma unroll
                 for (int tile = 0; tile < 3; ++tile) acc[nt][tile][0] = acc[nt][tile][1] = acc[nt][tile][2] = acc[nt][tile][3] = 0.0f;
             }
@@ -224,43 +256,53 @@ __global__ void __launch_bounds__(128, 2) gru_mma_kernel(const GruArgs a)
                     for (int nt = 0; nt < NT; ++nt)
                         mma_sync<FMT>(acc[nt][tile], areg[tile][ks], breg[nt][2 * ks], breg[nt][2 * ks + 1]);
 
+            // ---- head of the PREVIOUS step from the same B fragments (see `ahead`) -------------------------------
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                float ch[4];
+                head_mma(breg[nt], ch);
+                if (tt > 0 && gid == 0)
+                    *reinterpret_cast<float2*>(yp + (warp * CH + tt - 1) * C::YP_LD + nt * 8 + 2 * tig) =
+                        make_float2(ch[0] + ch[2], ch[1] + ch[3]);
+            }
             // ---- gates, state blend, rounded state for the next step, head partials ------------------------------
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) {
                 const float2 xv = *reinterpret_cast<const float2*>(xcur + tt * S + nt * 8 + 2 * tig);
-                float p[2] = {0.0f, 0.0f};
+                float z[2][2], dn[2][2], hn[2][2];
 #pragma unroll
                 for (int u = 0; u < 2; ++u)
 #pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const float x = e ? xv.y : xv.x;
-                        const float ar = acc[nt][u][e], az = acc[nt][u][2 + e], an = acc[nt][2][2 * u + e];
-                        const float er = ex2_approx(ar + fmaf(cr_w[u], x, cr_b[u]));
-                        const float ez = ex2_approx(az + fmaf(cz_w[u], x, cz_b[u]));
-                        const float r = rcp_approx(1.0f + er);
-                        const float z = rcp_approx(1.0f + ez);
-                        const float en = ex2_approx(fmaf(r, an + ch_b[u], fmaf(cn_w[u], x, cn_b[u])));
-                        const float nn = fmaf(-2.0f, rcp_approx(1.0f + en), 1.0f);
-                        const float hn = fmaf(z, hst[nt][u][e] - nn, nn);
-                        hst[nt][u][e] = hn;
-                        p[e] = fmaf(wo[u], hn, p[e]);
-                        store_state<FMT>(hnext + (nt * 8 + 2 * tig + e) * F::ROW_BYTES, u ? u1 : u0, hn);
-                    }
-                // head: sum over the warp's 16 units = over gid (lane bits 2..4)
+                    for (int e = 0; e < 2; ++e)
+                        gates_rz_dn(uc[u], acc[nt][u][e], acc[nt][u][2 + e], acc[nt][2][2 * u + e], e ? xv.y : xv.x,
+                                    z[u][e], dn[u][e]);
 #pragma unroll
-                for (int m = 4; m <= 16; m <<= 1) {
-                    p[0] += __shfl_xor_sync(0xffffffffu, p[0], m);
-                    p[1] += __shfl_xor_sync(0xffffffffu, p[1], m);
-                }
-                if (gid == 0) {
-                    yp[(warp * CH + tt) * C::YP_LD + nt * 8 + 2 * tig] = p[0];
-                    yp[(warp * CH + tt) * C::YP_LD + nt * 8 + 2 * tig + 1] = p[1];
+                for (int e = 0; e < 2; ++e)        // the two hidden units of one stream share the n-gate reciprocal
+                    gates_blend2(z[0][e], dn[0][e], hst[nt][0][e], z[1][e], dn[1][e], hst[nt][1][e], hn[0][e], hn[1][e]);
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    hst[nt][0][e] = hn[0][e];
+                    hst[nt][1][e] = hn[1][e];
+                    store_state2<FMT>(hnext + (nt * 8 + 2 * tig + e) * F::ROW_BYTES, u0, hn[0][e], hn[1][e]);
                 }
             }
             cur ^= 1;
             __syncthreads();                   // next state tile published; all reads of the old one are done
         }
 
+        if (n > 0) {                           // head of the chunk's last step: one more MMA on the final state tile
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                uint32_t bfin[BW];
+                float ch[4];
+                load_bfrag(hb + cur * C::HB_BYTES, nt, bfin);
+                head_mma(bfin, ch);
+                if (gid == 0)
+                    *reinterpret_cast<float2*>(yp + (warp * CH + n - 1) * C::YP_LD + nt * 8 + 2 * tig) =
+                        make_float2(ch[0] + ch[2], ch[1] + ch[3]);
+            }
+            __syncthreads();
+        }
         // ---- flush the chunk: y = sum of the four warps' partials + bias (+ x) ------------------------------------
         for (int idx = tid; idx < S * CH; idx += 128) {
             const int s = idx / CH, tt = idx % CH;
@@ -296,7 +338,7 @@ __global__ void __launch_bounds__(128, 2) gru_mma_kernel(const GruArgs a)
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int s = nt * 8 + 2 * tig + e;
-                if (s < ns) a.h_out[(b0 + s) * 64 + (u ? u1 : u0)] = hst[nt][u][e];
+                if (s < ns) a.h_out[(b0 + s) * 64 + u0 + u] = hst[nt][u][e];
             }
     if (delay) {
         __syncthreads();

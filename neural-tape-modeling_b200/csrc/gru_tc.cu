@@ -20,7 +20,7 @@
 // group's MMA latency with the other group's epilogue.  x / y are staged per 32-step chunk in shared memory.
 #include <string.h>
 
-#include "ntm_common.cuh"
+#include "gates.cuh"
 #include "tc_prims.cuh"
 
 namespace ntm {
@@ -183,14 +183,8 @@ __global__ void __launch_bounds__(32 * 5 * G, 1) gru_tc_kernel(const GruArgs a)
 
             // per-unit constants, pre-scaled like the packed weights
             const float* __restrict__ blob = a.blob;
-            const float cr_w = -LOG2E * blob[BlobLayout::W_IH + j];
-            const float cr_b = -LOG2E * (blob[BlobLayout::B_IH + j] + blob[BlobLayout::B_HH + j]);
-            const float cz_w = -LOG2E * blob[BlobLayout::W_IH + 64 + j];
-            const float cz_b = -LOG2E * (blob[BlobLayout::B_IH + 64 + j] + blob[BlobLayout::B_HH + 64 + j]);
-            const float cn_w = 2.0f * LOG2E * blob[BlobLayout::W_IH + 128 + j];
-            const float cn_b = 2.0f * LOG2E * blob[BlobLayout::B_IH + 128 + j];
-            const float ch_b = 2.0f * LOG2E * blob[BlobLayout::B_HH + 128 + j];
-            const float wo = blob[BlobLayout::W_OUT + j];
+            const UnitConst uc = load_unit_const(blob, j);
+            const float wo = uc.wo;
             const float bo = blob[BlobLayout::B_OUT];
 
             const bool delay = a.d != nullptr;
@@ -250,17 +244,19 @@ __global__ void __launch_bounds__(32 * 5 * G, 1) gru_tc_kernel(const GruArgs a)
                         }
                         tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < SC; ++i) {
-                            const float er = ex2_approx(__uint_as_float(ar[i]) + fmaf(cr_w, xv[i], cr_b));
-                            const float ez = ex2_approx(__uint_as_float(az[i]) + fmaf(cz_w, xv[i], cz_b));
-                            const float r = rcp_approx(1.0f + er);
-                            const float z = rcp_approx(1.0f + ez);
-                            const float en = ex2_approx(fmaf(r, __uint_as_float(an[i]) + ch_b, fmaf(cn_w, xv[i], cn_b)));
-                            const float nn = fmaf(-2.0f, rcp_approx(1.0f + en), 1.0f);
-                            const float hn = fmaf(z, hst[c0 + i] - nn, nn);       // (1 - z) n + z h
-                            hst[c0 + i] = hn;
-                            p[c0 + i] = wo * hn;
-                            store_operand<FMT>(bop + kmajor_off<C::ELT>(half * NS + c0 + i, j, C::B_LBO, C::B_SBO), hn);
+                        for (int i = 0; i < SC; i += 2) {
+                            float z0, z1, dn0, dn1, hn0, hn1;
+                            gates_rz_dn(uc, __uint_as_float(ar[i]), __uint_as_float(az[i]), __uint_as_float(an[i]), xv[i], z0, dn0);
+                            gates_rz_dn(uc, __uint_as_float(ar[i + 1]), __uint_as_float(az[i + 1]), __uint_as_float(an[i + 1]),
+                                        xv[i + 1], z1, dn1);
+                            hn0 = gates_blend1(z0, dn0, hst[c0 + i]);
+                            hn1 = gates_blend1(z1, dn1, hst[c0 + i + 1]);
+                            hst[c0 + i] = hn0;
+                            hst[c0 + i + 1] = hn1;
+                            p[c0 + i] = wo * hn0;
+                            p[c0 + i + 1] = wo * hn1;
+                            store_operand<FMT>(bop + kmajor_off<C::ELT>(half * NS + c0 + i, j, C::B_LBO, C::B_SBO), hn0);
+                            store_operand<FMT>(bop + kmajor_off<C::ELT>(half * NS + c0 + i + 1, j, C::B_LBO, C::B_SBO), hn1);
                         }
                     }
                     // release the next MMA of this group, then do the head off the critical path

@@ -36,6 +36,15 @@ def _stream(device):
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+def _host_out(out, shape, name):
+    """Result buffer of a *_host call: a fresh pinned tensor, or the caller's contiguous float32 host tensor."""
+    if out is None:
+        return torch.empty(shape, dtype=torch.float32, pin_memory=True)
+    if out.is_cuda or out.dtype != torch.float32 or tuple(out.shape) != tuple(shape) or not out.is_contiguous():
+        raise RuntimeError(f"{name}: expected a contiguous float32 host tensor of shape {tuple(shape)}")
+    return out
+
+
 def _as_rows(t, name):
     """(B, 1, T) tensor -> float32 view with unit stride in T; returns (tensor, B, T, ld)."""
     if t.dim() != 3 or t.shape[1] != 1:
@@ -178,10 +187,11 @@ class RNN(torch.nn.Module):
             self.hidden = self.hidden.expand(1, B, self.hidden_size).contiguous()
         return self.forward(input)
 
-    def predict_host(self, input, chunk=0):
+    def predict_host(self, input, chunk=0, out=None):
         """predict() for a HOST tensor (pinned for full speed): chunked H2D / kernel / D2H pipeline inside the
-        engine (ntm_gru_predict_host).  Returns a pinned host tensor.  This is the end-to-end call the bench times
-        (host->device at code/test-model.py:427-433, device->host at :525)."""
+        engine (ntm_gru_predict_host).  Returns a pinned host tensor (`out` if given: page-locking a fresh
+        multi-GB result buffer costs seconds, so repeated callers pass their own).  This is the end-to-end call the
+        bench times (host->device at code/test-model.py:427-433, device->host at :525)."""
         if input.is_cuda or input.dim() != 3 or input.shape[1] != 1:
             raise RuntimeError("predict_host expects a host tensor of shape (N_BATCHES, 1, N_SAMPLES)")
         dev = self._device()
@@ -191,7 +201,7 @@ class RNN(torch.nn.Module):
         self.initialize_hidden()
         self.warm_start()
         h = self.hidden.reshape(1, self.hidden_size).expand(B, self.hidden_size).contiguous().cpu()
-        y = torch.empty((B, 1, T), dtype=torch.float32, pin_memory=True)
+        y = _host_out(out, (B, 1, T), "out")
         rc = _lib.load().ntm_gru_predict_host(handle, _lib.MODES[self.mode], _ptr(x), _ptr(y), _ptr(h), B, T,
                                               int(bool(self.skip)), int(chunk))
         _lib.check(rc)
@@ -320,8 +330,9 @@ class DiffDelRNN(RNN):
             self.diffdel.buffer = self.diffdel.buffer.expand(B, 1, -1).contiguous()
         return self.forward(input, d_traj)
 
-    def predict_host(self, input, d_traj, chunk=0):
-        """predict() for HOST tensors through ntm_diffdel_predict_host; returns pinned host (output, output_pre_d)."""
+    def predict_host(self, input, d_traj, chunk=0, out=None, out_pre_d=None):
+        """predict() for HOST tensors through ntm_diffdel_predict_host; returns pinned host (output, output_pre_d)
+        (`out` / `out_pre_d` if given)."""
         if input.is_cuda or d_traj.is_cuda or input.dim() != 3 or input.shape[1] != 1:
             raise RuntimeError("predict_host expects host tensors of shape (N_BATCHES, 1, N_SAMPLES)")
         dev = self._device()
@@ -334,8 +345,8 @@ class DiffDelRNN(RNN):
         D = int(self.diffdel.max_delay)
         h = self.hidden.reshape(1, self.hidden_size).expand(B, self.hidden_size).contiguous().cpu()
         hist = self.diffdel.buffer.reshape(1, D).expand(B, D).contiguous().cpu()
-        y = torch.empty((B, 1, T), dtype=torch.float32, pin_memory=True)
-        pre = torch.empty((B, 1, T), dtype=torch.float32, pin_memory=True)
+        y = _host_out(out, (B, 1, T), "out")
+        pre = _host_out(out_pre_d, (B, 1, T), "out_pre_d")
         rc = _lib.load().ntm_diffdel_predict_host(handle, _lib.MODES[self.mode], _ptr(x), _ptr(d), _ptr(y), _ptr(pre),
                                                   _ptr(h), _ptr(hist), B, T, D, int(bool(self.skip)), int(chunk))
         _lib.check(rc)

@@ -298,7 +298,7 @@ def test_cfg2_width_properties():
     with torch.inference_mode():
         y = m.predict(x)
         halves = torch.cat([m.predict(x[:512]), m.predict(x[512:])], 0)
-        assert float((halves - y).abs().max()) < 3e-6      # the dispatcher may pick another k-split for 512 streams
+        assert float((halves - y).abs().max()) <= TOL      # the dispatcher may pick another k-split for 512 streams
         lib.load().ntm_set_tuning(4, 4)
         assert torch.equal(torch.cat([m.predict(x[:512]), m.predict(x[512:])], 0), m.predict(x))
         lib.load().ntm_set_tuning(0, 0)
