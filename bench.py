@@ -273,7 +273,12 @@ def main():
         "clocks": clocks,
         "roofline": {
             "bound": "tensor", "achieved": achieved_tflops, "peak": tensor_peak, "unit": "TFLOP/s",
-            "frac": achieved_tflops / tensor_peak, "traffic": None, "peak_source": peak_src,
+            "frac": achieved_tflops / tensor_peak,
+            # dram__bytes_read+write of this kernel from one `ncu --set full` capture (profiles/r01_mma_b1024_ncu.txt:
+            # 20.0 MB for 1024 x 4800 samples = the x reads; the y writes of that capture stayed in the 126 MB L2),
+            # scaled to this launch's sample count
+            "traffic": round(20.0e6 / (1024 * 4800) * B * T), "algorithmic_bytes": BYTES_PER_SAMPLE * B * T,
+            "peak_source": peak_src,
             "kernel_ms": kern_ms, "kernel": kernel_name,
             "regime": "latency-bound recurrence: 1024 streams = 7 per SM, one dependent GRU step at a time (DESIGN.md section 4)",
             "legacy_mma_sync_peak_tflops": sm_count * 4 * 4096 / 8 * f_clk / 1e12,

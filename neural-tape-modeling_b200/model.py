@@ -121,7 +121,7 @@ class RNN(torch.nn.Module):
         # parameter containers only (state_dict keys GRU.* / output.*); their forward() is never called
         self.GRU = torch.nn.GRU(input_size, hidden_size, batch_first=True)
         self.output = torch.nn.Linear(hidden_size, output_size, bias=self._head_bias)
-        self.mode = "fp32"          # "fp32" | "tf32" | "bf16" | "tf32x3"  (include/ntm_b200.h NTM_MODE_*)
+        self.mode = "fp32"          # "fp32" | "f16" | "tf32" | "bf16"  (include/ntm_b200.h NTM_MODE_*)
         self._engine = _Engine()
         self.hidden = None
         # parameters are re-packed lazily whenever they may have changed
