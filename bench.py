@@ -343,7 +343,7 @@ def aux_measurements(ntm_b200, signals, dev, mode):
         mb.mode = md
         per_mode[md] = timed(x2, mb)
     mb.mode = "f16"
-    per_mode["f16_tcgen05_kernel"] = timed(x2, mb, (8, 1))
+    per_mode["f16_tcgen05_kernel"] = timed(x2, mb, (32, 2))
     out["cfg2_samples_per_s_by_mode"] = per_mode
     del x2
     # throughput regime (cfg 4 per-GPU widths): both tensor-core kernels
@@ -351,7 +351,7 @@ def aux_measurements(ntm_b200, signals, dev, mode):
     for Bb, Tb in ((8192, 12000), (65536, 3000)):
         xb = signals.stream_batch_device(Bb, Tb, dev, dur=10.0).reshape(Bb, 1, Tb)
         mb.mode = "f16"
-        big[str(Bb)] = {"mma_sync": timed(xb, mb, (8, 3)), "tcgen05": timed(xb, mb, (64, 2))}
+        big[str(Bb)] = {"mma_sync": timed(xb, mb, (8, 3)), "tcgen05": timed(xb, mb, (32, 2))}
         mb.mode = "fp32"
         big[str(Bb)]["fp32_cuda_core"] = timed(xb, mb)
         del xb

@@ -77,7 +77,8 @@ int run_gru(Handle* hd, int mode, const ntm::GruArgs& a, cudaStream_t st)
         // latency regime (few streams per SM): warp-level mma.sync kernel; throughput regime: tcgen05 kernel.
         // ntm_set_tuning(n, 3) forces the former with n/8 tiles per CTA, (n, 1|2) the latter.
         const int tg = g_tune_ks & 0xff;
-        const bool use_mma = tg == 3 || (tg == 0 && a.B <= (long long)hd->sm_count * g_mma_streams_per_sm);
+        // (tf32 operands exist only in the mma.sync kernel)
+        const bool use_mma = tg == 3 || fmt == 2 || (tg == 0 && a.B <= (long long)hd->sm_count * g_mma_streams_per_sm);
         if (use_mma) {
             const int nt = g_tune_s > 0 && tg == 3 ? g_tune_s / 8 : 1;
             CU(ntm::launch_gru_mma(a, fmt, nt, st));
@@ -279,7 +280,7 @@ int ntm_gru_prepare(const float* w_ih, const float* w_hh, const float* b_ih, con
     memcpy(host + L::B_HH, b_hh, sizeof(float) * ntm::G192);
     memcpy(host + L::W_OUT, w_out, sizeof(float) * ntm::H64);
     host[L::B_OUT] = b_out ? b_out[0] : 0.0f;
-    ntm::pack_tc_images(w_hh, host);
+    ntm::pack_tc_images(host);
 
     Handle* hd = new (std::nothrow) Handle();
     if (!hd) { delete[] host; return NTM_ENOMEM; }

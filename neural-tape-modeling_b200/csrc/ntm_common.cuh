@@ -17,13 +17,12 @@ struct BlobLayout {
     static constexpr int W_OUT = B_HH + G192;         // 64
     static constexpr int B_OUT = W_OUT + H64;         // 1 (0 when the head has no bias)
     static constexpr int FP32_END = B_OUT + 4;
-    // tensor-core A-operand images (gru_tc.cu): 3 gate tiles x 128 rows x 64 k, K-major core-matrix layout,
-    // rows pre-scaled; f16 and bf16 take 2 bytes per element, tf32 4
+    // tensor-core A-operand images (gru_tc.cu): 3 gate tiles x 128 rows x 80 k (64 + the input/bias augmentation) of
+    // 2-byte elements, row-major; one image per operand format
     static constexpr int IMG_F16 = FP32_END;
-    static constexpr int IMG_BF16 = IMG_F16 + 3 * 128 * 64 / 2;
-    static constexpr int IMG_TF32 = IMG_BF16 + 3 * 128 * 64 / 2;
-    static constexpr int TOTAL = IMG_TF32 + 3 * 128 * 64;
-    __host__ __device__ static constexpr int tc_image(int fmt) { return fmt == 2 ? IMG_TF32 : fmt == 1 ? IMG_BF16 : IMG_F16; }
+    static constexpr int IMG_BF16 = IMG_F16 + 3 * 128 * 80 / 2;
+    static constexpr int TOTAL = IMG_BF16 + 3 * 128 * 80 / 2;
+    __host__ __device__ static constexpr int tc_image(int fmt) { return fmt == 1 ? IMG_BF16 : IMG_F16; }
 };
 static_assert(BlobLayout::FP32_END % 4 == 0, "tensor-core images must stay 16-byte aligned");
 
@@ -48,7 +47,7 @@ struct GruArgs {
 cudaError_t launch_gru_fp32(const GruArgs& a, int sm_count, int tune_s, int tune_ks, int fast_act, cudaStream_t st);
 cudaError_t launch_gru_tc(const GruArgs& a, int fmt, int sm_count, int tune_n, int tune_g, cudaStream_t st);
 cudaError_t launch_gru_mma(const GruArgs& a, int fmt, int n_tiles, cudaStream_t st);
-void pack_tc_images(const float* w_hh, float* blob_host);   // host: fills BlobLayout::IMG_* from PyTorch-layout W_hh
+void pack_tc_images(float* blob_host);   // host: fills BlobLayout::IMG_* from the fp32 part of the blob
 cudaError_t launch_delay(const float* x, long long ldx, const float* d, long long ldd, float* y, long long ldy,
                          const float* hist_in, float* hist_out, long long B, long long T, long long D, int warmup,
                          cudaStream_t st);

@@ -25,7 +25,7 @@ with torch.inference_mode():
     for tag in ("cfg1", "cfg2"):
         g = load_golden(f"golden_{tag}")
         for mode in ["fp32"] + modes + [mm + "/mma" for mm in modes]:
-            lib.load().ntm_set_tuning(8, 3) if mode.endswith("/mma") else lib.load().ntm_set_tuning(0 if mode == "fp32" else 8, 0 if mode == "fp32" else 1)
+            lib.load().ntm_set_tuning(8, 3) if mode.endswith("/mma") else lib.load().ntm_set_tuning(0 if mode == "fp32" else 32, 0 if mode == "fp32" else 2)
             mode = mode.split("/")[0]
             m = ntm_b200.RNN(1, 64, 1, False).to(dev)
             m.load_state_dict(load_ckpt(tag))
@@ -49,7 +49,7 @@ with torch.inference_mode():
         yref = m.predict(x[:, :, :4800])
         for mode in modes:
             m.mode = mode
-            for (n, g_) in ((0, 0), (8, 1), (16, 1), (32, 1), (64, 1), (8, 2), (16, 2), (32, 2), (64, 2), (8, 3), (16, 3)):
+            for (n, g_) in ((0, 0), (32, 1), (64, 1), (32, 2), (64, 2), (8, 3), (16, 3)):
                 if B // max(n * g_, 1) > 20000:
                     continue
                 L.ntm_set_tuning(n, g_)

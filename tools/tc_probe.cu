@@ -18,7 +18,7 @@ struct Args {
     const float* B;
     float* D;
     long long* cyc;
-    int N, ts, swap, iters, reps;
+    int N, ts, swap, iters, reps, bmn;
 };
 
 template <int FMT>
@@ -55,7 +55,14 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(Args p)
     for (int idx = tid; idx < N * 64; idx += 128) {
         const int n = idx / 64, k = idx % 64;
         const float v = p.B[idx];
-        if (FMT == FMT_TF32) *(uint32_t*)(sB + kmajor_off<4>(n, k, lboB, sbo)) = to_tf32(v);
+        if (p.bmn) {
+            // MN-major B, no swizzle: 16-byte vectors of T consecutive n; 8 consecutive k at 16-byte stride (one 128-byte
+            // core matrix); n-vector groups at SBO = 128, k groups of 8 at LBO = (N / T) * 128
+            constexpr int T = 16 / ELT;
+            const uint32_t off = (uint32_t)(n % T) * ELT + (uint32_t)(k % 8) * 16 + (uint32_t)(n / T) * 128 + (uint32_t)(k / 8) * ((uint32_t)(N / T) * 128);
+            if (FMT == FMT_TF32) *(uint32_t*)(sB + off) = to_tf32(v);
+            else *(__nv_bfloat16*)(sB + off) = __float2bfloat16_rn(v);
+        } else if (FMT == FMT_TF32) *(uint32_t*)(sB + kmajor_off<4>(n, k, lboB, sbo)) = to_tf32(v);
         else *(__nv_bfloat16*)(sB + kmajor_off<2>(n, k, lboB, sbo)) = __float2bfloat16_rn(v);
     }
     if (!p.ts) {
@@ -89,15 +96,19 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(Args p)
     // ---- MMA issue ---------------------------------------------------------------------------------
     if (tid == 0) {
         tc_fence_after();
-        const uint32_t idesc = instr_desc(FMT, 128, N);
+        const uint32_t idesc = instr_desc(FMT, 128, N) | (p.bmn ? (1u << 16) : 0u);
         const uint32_t aL = p.swap ? sbo : lboA, aS = p.swap ? lboA : sbo;
-        const uint32_t bL = p.swap ? sbo : lboB, bS = p.swap ? lboB : sbo;
+        constexpr int TB = 16 / ELT;
+        const uint32_t lboB_mn = (uint32_t)(N / TB) * 128;          // k-group (8 k) stride
+        const uint32_t bL = p.bmn ? (p.swap ? 128u : lboB_mn) : (p.swap ? sbo : lboB);
+        const uint32_t bS = p.bmn ? (p.swap ? lboB_mn : 128u) : (p.swap ? lboB : sbo);
+        const uint32_t bstep = p.bmn ? (KSTEP / 8) * lboB_mn : 2 * lboB;   // bytes between consecutive MMAs along K
         long long t_issue = 0;
         const long long t0 = clock64();
         for (int it = 0; it < p.iters; ++it) {
             for (int rep = 0; rep < p.reps; ++rep) {
                 for (int ks = 0; ks < NK; ++ks) {
-                    const uint64_t bd = smem_desc(smem_u32(sB) + ks * 2 * lboB, bL, bS);
+                    const uint64_t bd = smem_desc(smem_u32(sB) + ks * bstep, bL, bS);
                     if (p.ts) mma_ts<FMT>(tmem, tmem + colA + ks * 8, bd, idesc, ks > 0);
                     else mma_ss<FMT>(tmem, smem_desc(smem_u32(sA) + ks * 2 * lboA, aL, aS), bd, idesc, ks > 0);
                 }
@@ -318,6 +329,7 @@ int main(int argc, char** argv)
     a.swap = atoi(argv[4]);
     a.iters = atoi(argv[5]);
     a.reps = atoi(argv[6]);
+    a.bmn = argc > 7 ? atoi(argv[7]) : 0;
     const int N = a.N;
     std::vector<float> A(128 * 64), B(N * 64), D(128 * N);
     srand(1234);
@@ -358,8 +370,8 @@ int main(int argc, char** argv)
             maxerr = fmax(maxerr, fabs(s - D[m * N + n]));
             maxref = fmax(maxref, fabs(s));
         }
-    printf("%s ts=%d N=%3d swap=%d iters=%d reps=%d : max|err|=%.3e (max|ref|=%.2f) %s   cycles/iter=%.1f first-issue=%lld\n",
-           argv[1], a.ts, N, a.swap, a.iters, a.reps, maxerr, maxref, maxerr < 1e-4 ? "OK " : "BAD",
+    printf("%s ts=%d N=%3d swap=%d iters=%d reps=%d bmn=%d : max|err|=%.3e (max|ref|=%.2f) %s   cycles/iter=%.1f first-issue=%lld\n",
+           argv[1], a.ts, N, a.swap, a.iters, a.reps, a.bmn, maxerr, maxref, maxerr < 1e-4 ? "OK " : "BAD",
            (double)cyc[0] / a.iters, cyc[1]);
     if (maxerr >= 1e-4) {
         printf("  D[0][0..7]   =");
