@@ -322,6 +322,35 @@ def aux_measurements(ntm_b200, signals, dev, mode):
         m1(x1[:, :, 64 * k:64 * k + 64])
     torch.cuda.synchronize(dev)
     out["batch1_block64_ns_per_sample_incl_launch"] = (time.perf_counter() - t0) * 1e9 / (nblk * 64)
+    # the same through the block-stream API (one C call per block), exact fp32 and f16 tensor-core arithmetic
+    for md in ("fp32", "f16"):
+        m1.mode = md
+        m1.initialize_hidden(); m1.warm_start()
+        bs = m1.block_stream(1, 64)
+        blocks = [x1[:, :, 64 * k:64 * k + 64] for k in range(nblk)]
+        for k in range(50):
+            bs.process(blocks[k])
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for k in range(nblk):
+            bs.process(blocks[k])
+        torch.cuda.synchronize(dev)
+        out[f"batch1_block64_ns_per_sample_blockstream_{md}"] = (time.perf_counter() - t0) * 1e9 / (nblk * 64)
+        # per-block latency: submit one block, wait for it (what a real-time callback sees)
+        lat = []
+        for k in range(200):
+            t1 = time.perf_counter()
+            bs.process(blocks[k])
+            torch.cuda.synchronize(dev)
+            lat.append(time.perf_counter() - t1)
+        lat.sort()
+        out[f"batch1_block64_latency_us_median_{md}"] = lat[len(lat) // 2] * 1e6
+    m1.mode = "fp32"
+    m1.initialize_hidden(); m1.warm_start()
+    m1.mode = "f16"
+    e0.record(); m1(x1); e1.record(); torch.cuda.synchronize(dev)
+    out["batch1_kernel_ns_per_sample_f16"] = e0.elapsed_time(e1) * 1e6 / 480000
+    m1.mode = "fp32"
     from ntm_b200 import lib
     L = lib.load()
     mb = ntm_b200.RNN(1, 64, 1, False).to(dev)
@@ -356,6 +385,22 @@ def aux_measurements(ntm_b200, signals, dev, mode):
         big[str(Bb)]["fp32_cuda_core"] = timed(xb, mb)
         del xb
     out["large_batch_samples_per_s"] = big
+    # cfg 3: DiffDelGRU (GRU + fused fractional-delay read), 256 streams x 30 s, predict() semantics
+    Bd, Td = 256, 30 * FS
+    md = ntm_b200.DiffDelRNN(1, 64, 1, False, max_delay=signals.DELAY_MAX).to(dev)
+    md.load_state_dict(load_sd("cfg3"))
+    xd = signals.stream_batch_device(Bd, Td, dev, dur=30.0).reshape(Bd, 1, Td)
+    dd = signals.delay_trajectory_device(Bd, Td, dev).reshape(Bd, 1, Td)
+    md.diffdel.check_delay = False            # the reference's assert costs a full extra pass + a stream sync
+    cfg3 = {}
+    for mdm in ("fp32", "f16"):
+        md.mode = mdm
+        md.predict(xd[:, :, :4800], dd[:, :, :4800])
+        torch.cuda.synchronize(dev)
+        e0.record(); yd, pd = md.predict(xd, dd); e1.record(); torch.cuda.synchronize(dev)
+        cfg3[mdm] = Bd * Td / (e0.elapsed_time(e1) * 1e-3)
+        del yd, pd
+    out["cfg3_diffdel_256x30s_samples_per_s"] = cfg3
     return out
 
 

@@ -88,7 +88,7 @@ struct MmaCfg {
 };
 
 template <int FMT, int NT>
-__global__ void __launch_bounds__(128, 2) gru_mma_kernel(const GruArgs a)
+__global__ void __launch_bounds__(128, FMT == FMT_TF32 ? 2 : 4) gru_mma_kernel(const GruArgs a)
 {
     using C = MmaCfg<FMT, NT>;
     using F = Frag<FMT>;

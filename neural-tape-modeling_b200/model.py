@@ -169,12 +169,18 @@ class RNN(torch.nn.Module):
         h_in = self._hidden_in(B, dev)
         y = torch.empty((B, 1, T), dtype=torch.float32, device=dev)
         h_out = torch.empty((1, B, self.hidden_size), dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
-            rc = _lib.load().ntm_gru_forward(handle, _lib.MODES[self.mode], _ptr(x), ldx, _ptr(y), max(T, 1),
-                                             _ptr(h_in), _ptr(h_out), B, T, int(bool(self.skip)), _stream(dev))
-        _lib.check(rc)
+        # (no torch.cuda.device() context: the C ABI switches to the handle's device itself)
+        rc = _lib.load().ntm_gru_forward(handle, _lib.MODES[self.mode], _ptr(x), ldx, _ptr(y), max(T, 1),
+                                         _ptr(h_in), _ptr(h_out), B, T, int(bool(self.skip)), _stream(dev))
+        if rc:
+            _lib.check(rc)
         self.hidden = h_out
         return y
+
+    def block_stream(self, n_streams=1, block_len=64):
+        """Real-time block mode (BASELINE.json cfg 5): consecutive `forward` calls on short blocks with carried state,
+        with the per-call host work stripped to one C call -- see BlockStream."""
+        return BlockStream(self, n_streams, block_len)
 
     def predict(self, input):
         """Zero state -> warm start -> whole signal (code/model.py:218-246), for any number of streams."""
@@ -207,6 +213,50 @@ class RNN(torch.nn.Module):
         _lib.check(rc)
         self.hidden = h.reshape(1, B, self.hidden_size).to(dev)
         return y
+
+
+class BlockStream:
+    """Block-by-block processing of `n_streams` streams with the state carried on the device.
+
+    Semantically identical to calling `model(x_block)` repeatedly (code/model.py:67-88 with `self.hidden` carried,
+    SURVEY.md section 9.3 #1): the state starts from `model.hidden` (zeros if None, i.e. after `initialize_hidden()`;
+    call `warm_start()` first for `predict()` semantics) and is written back by `close()`.  Buffers, raw pointers, the
+    handle and the CUDA stream are resolved once, so a block costs one ctypes call + one kernel launch."""
+
+    def __init__(self, model, n_streams, block_len):
+        dev = model._device()
+        if dev.type != "cuda":
+            raise RuntimeError("ntm_b200 has no CPU path; move the model to a CUDA device")
+        self.model, self.B, self.T, self.device = model, int(n_streams), int(block_len), dev
+        self._handle = model._handle(dev)
+        self._mode = _lib.MODES[model.mode]
+        self._skip = int(bool(model.skip))
+        h = model._hidden_in(self.B, dev)
+        self.h = torch.zeros((1, self.B, model.hidden_size), dtype=torch.float32, device=dev) if h is None else h.clone()
+        self.y = torch.empty((self.B, 1, self.T), dtype=torch.float32, device=dev)
+        self._fn = _lib.load().ntm_gru_forward
+        self._hp = ctypes.c_void_p(self.h.data_ptr())
+        self._yp = ctypes.c_void_p(self.y.data_ptr())
+        self._st = _stream(dev)
+
+    def process(self, x, out=None):
+        """x (n_streams, 1, block_len) float32 on the model's device -> y (the internal buffer, overwritten by the
+        next call, or `out`).  Asynchronous on the stream that was current when the BlockStream was created."""
+        if x.dtype != torch.float32 or not x.is_cuda or x.dim() != 3 or x.shape[0] != self.B or x.shape[2] > self.T \
+                or x.stride(2) != 1:
+            raise RuntimeError(f"expected a float32 CUDA block of shape ({self.B}, 1, <= {self.T})")
+        T = x.shape[2]
+        y, yp = (self.y, self._yp) if out is None else (out, ctypes.c_void_p(out.data_ptr()))
+        rc = self._fn(self._handle, self._mode, ctypes.c_void_p(x.data_ptr()), x.stride(0) if self.B > 1 else max(T, 1),
+                      yp, y.stride(0) if self.B > 1 else max(T, 1), self._hp, self._hp, self.B, T, self._skip, self._st)
+        if rc:
+            _lib.check(rc)
+        return y if T == y.shape[2] else y[:, :, :T]
+
+    def close(self):
+        """Hand the carried state back to the model (`model.hidden`)."""
+        self.model.hidden = self.h
+        return self.model.hidden
 
 
 class TimeVaryingDelayLine(torch.nn.Module):

@@ -140,6 +140,38 @@ def test_rnn_batch_vs_oracle():
     assert abs(c_oracle.esr(y.numpy(), yr.numpy())) <= 1e-9
 
 
+@pytest.mark.parametrize("mode", ["fp32", "f16"])
+def test_block_stream_equals_one_call(mode):
+    """cfg 5 semantics: 64-sample blocks with carried state == one long forward (bit for bit), and == repeated
+    forward() calls; the block stream hands its state back to the model."""
+    m = make_rnn("cfg1", mode=mode)
+    x = dev(signals.signal("sweepnoise", 64 * 40 + 17, seed=3)).reshape(1, 1, -1)
+    with torch.inference_mode():
+        m.initialize_hidden()
+        m.warm_start()
+        h0 = m.hidden.clone()
+        y_all = m(x)
+        h_all = m.hidden.clone()
+        m.hidden = h0.clone()
+        bs = m.block_stream(1, 64)
+        parts = [bs.process(x[:, :, s:s + 64]).clone() for s in range(0, x.shape[2], 64)]
+        assert torch.equal(torch.cat(parts, 2), y_all)
+        assert torch.equal(bs.close(), h_all) and m.hidden is bs.h
+        m.hidden = h0.clone()
+        parts = [m(x[:, :, s:s + 64]) for s in range(0, x.shape[2], 64)]
+        assert torch.equal(torch.cat(parts, 2), y_all) and torch.equal(m.hidden, h_all)
+        # several streams, caller-provided output
+        B = 5
+        xb = dev(signals.stream_batch(B, 640)).reshape(B, 1, -1)
+        m.initialize_hidden()
+        y_ref = m(xb)
+        m.initialize_hidden()
+        bs = m.block_stream(B, 64)
+        out = torch.empty((B, 1, 64), device=DEV)
+        got = torch.cat([bs.process(xb[:, :, s:s + 64], out=out).clone() for s in range(0, 640, 64)], 2)
+        assert torch.equal(got, y_ref)
+
+
 def test_rnn_input_handling():
     m = make_rnn("cfg1")
     x = dev(signals.signal("noise", 512, seed=1)).reshape(1, 1, -1)
