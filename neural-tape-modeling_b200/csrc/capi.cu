@@ -15,8 +15,9 @@ namespace {
 constexpr unsigned HANDLE_MAGIC = 0x4e544d42u;   // "NTMB"
 thread_local int t_last_cuda = 0;
 int g_tune_s = 0, g_tune_ks = 0, g_tune_fast = 0;
-int g_last_kernel = -1;             // 0 fp32 CUDA-core, 1 warp-level mma.sync, 2 tcgen05 (ntm_query NTM_Q_LAST_KERNEL)
-long long g_mma_streams_per_sm = 1ll << 40;   // crossover between the two tensor-core kernels (measured)
+// 0 fp32 CUDA-core, 1 warp-level mma.sync, 2 tcgen05 weight-stationary, 3 tcgen05 stream-major (NTM_Q_LAST_KERNEL)
+int g_last_kernel = -1;
+long long g_tcs_min_streams_per_sm = 128;     // crossover mma.sync -> stream-major tcgen05 kernel
 
 struct HostPipe {            // staging of the *_host entry points
     cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
@@ -32,6 +33,7 @@ struct Handle {
     int sm_count;
     int has_bias;
     float* blob;
+    ntm::TcsConsts tcs;      // host copy of the stream-major kernel's constant-bank parameters
     HostPipe pipe;
 };
 
@@ -74,12 +76,18 @@ int run_gru(Handle* hd, int mode, const ntm::GruArgs& a, cudaStream_t st)
         g_last_kernel = 0;
     } else {
         const int fmt = mode == NTM_MODE_TF32 ? 2 : mode == NTM_MODE_BF16 ? 1 : 0;    // tc_prims.cuh FMT_*
-        // latency regime (few streams per SM): warp-level mma.sync kernel; throughput regime: tcgen05 kernel.
-        // ntm_set_tuning(n, 3) forces the former with n/8 tiles per CTA, (n, 1|2) the latter.
+        // latency regime (few streams per SM): warp-level mma.sync kernel; throughput regime (>= one 128-stream tile
+        // per SM, plain GRU, 16-bit operands): stream-major tcgen05 kernel.
+        // ntm_set_tuning(n, 3) forces mma.sync with n/8 tiles per CTA, (n, 1|2) the weight-stationary tcgen05 kernel,
+        // (tiles, 4) the stream-major tcgen05 kernel with 1 or 2 tiles per CTA.
         const int tg = g_tune_ks & 0xff;
-        // (tf32 operands exist only in the mma.sync kernel)
-        const bool use_mma = tg == 3 || fmt == 2 || (tg == 0 && a.B <= (long long)hd->sm_count * g_mma_streams_per_sm);
-        if (use_mma) {
+        const bool tcs_ok = fmt != 2 && a.d == nullptr;     // (tf32 operands exist only in the mma.sync kernel)
+        const bool use_tcs = tcs_ok && (tg == 4 || (tg == 0 && a.B >= (long long)hd->sm_count * g_tcs_min_streams_per_sm));
+        const bool use_mma = !use_tcs && (tg == 3 || tg == 4 || tg == 0 || fmt == 2);
+        if (use_tcs) {
+            CU(ntm::launch_gru_tcs(a, hd->tcs, fmt, hd->sm_count, tg == 4 ? g_tune_s : 0, st));
+            g_last_kernel = 3;
+        } else if (use_mma) {
             const int nt = g_tune_s > 0 && tg == 3 ? g_tune_s / 8 : 1;
             CU(ntm::launch_gru_mma(a, fmt, nt, st));
             g_last_kernel = 1;
@@ -281,12 +289,15 @@ int ntm_gru_prepare(const float* w_ih, const float* w_hh, const float* b_ih, con
     memcpy(host + L::W_OUT, w_out, sizeof(float) * ntm::H64);
     host[L::B_OUT] = b_out ? b_out[0] : 0.0f;
     ntm::pack_tc_images(host);
+    ntm::TcsConsts tcs;
+    ntm::fill_tcs_consts(host, &tcs);
 
     Handle* hd = new (std::nothrow) Handle();
     if (!hd) { delete[] host; return NTM_ENOMEM; }
     hd->magic = HANDLE_MAGIC;
     hd->device = device;
     hd->has_bias = b_out != nullptr;
+    hd->tcs = tcs;
     hd->blob = nullptr;
     cudaError_t e = cudaDeviceGetAttribute(&hd->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) e = cudaMalloc(&hd->blob, sizeof(float) * L::TOTAL);

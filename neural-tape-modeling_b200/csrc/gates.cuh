@@ -45,6 +45,18 @@ __device__ __forceinline__ void gates_rz_dn(const UnitConst& c, float ar, float 
     dn = 1.0f + ex2_approx(fminf(fmaf(r, an + c.ch_b, fmaf(c.cn_w, x, c.cn_b)), EX2_CLAMP));
 }
 
+// the same with complete pre-activations: ar, az already contain W_i x + b (K-augmented MMA), an = W_hn h + b_hn,
+// gin = W_in x + b_in (all scaled)
+__device__ __forceinline__ void gates_rz_dn_pre(float ar, float az, float an, float gin, float& z, float& dn)
+{
+    const float dr = 1.0f + ex2_approx(fminf(ar, EX2_CLAMP));
+    const float dz = 1.0f + ex2_approx(fminf(az, EX2_CLAMP));
+    const float rinv = rcp_approx(dr * dz);
+    const float r = dz * rinv;
+    z = dr * rinv;
+    dn = 1.0f + ex2_approx(fminf(fmaf(r, an, gin), EX2_CLAMP));
+}
+
 // new states of two pairs (their n-gate denominators share one reciprocal).  Only pair up the SAME stream (two hidden
 // units): a reciprocal shared between two streams would make a stream's rounding depend on its neighbour.
 __device__ __forceinline__ void gates_blend2(float z0, float dn0, float h0, float z1, float dn1, float h1, float& hn0, float& hn1)

@@ -1,0 +1,285 @@
+// Stream-major tensor-core persistent GRU kernel (tcgen05.mma + TMEM) -- the THROUGHPUT regime of the batched path
+// (>= ~128 streams per SM; BASELINE cfg 4: 65 536 streams).
+//
+// Replaces, for many concurrent streams, the per-timestep loop behind `self.GRU(x, self.hidden)` + `self.output(x)` of
+// RNN.forward (code/model.py:81-82; gate equations torch rnn.py:1221-1224).
+//
+// Formulation.  One tile = 128 streams = the M rows of the MMA.  Per timestep the tensor core evaluates
+//       G[128 streams x 192] = [H | x_hi x_lo x_hi 1 1 0..][128 x 80] . W^T[80 x 192]
+//   A operand  the rounded state of the tile, IN TENSOR MEMORY (".ts" MMA form): TMEM lane = stream, so the thread that
+//              owns a stream writes its new rounded state with tcgen05.st straight from registers -- no shared-memory
+//              round trip, no proxy fence, no cross-thread exchange anywhere in the step.
+//   B operand  W_hh (+ the K augmentation carrying W_i x + b for r, z and b_hn for n), K-major, staged once in shared
+//              memory from the image ntm_gru_prepare packed (rows pre-scaled by -log2 e / 2 log2 e).
+//   N = 192    five MMAs of M=128, N=192, K=16 per tile-step run at the tensor pipe's full rate (measured 106 clk each,
+//              profiles/r01_tc_probe.txt) = 4 clk per stream-step, against >= 16 clk per stream-step of MUFU work: the
+//              tensor pipe is never the bound here, which the weight-stationary kernel (gru_tc.cu) could not achieve.
+//   epilogue   accumulator lane = stream, column = gate row: ONE THREAD OWNS ONE STREAM -- its 64 fp32 states live in
+//              registers for the whole launch, r/z/n of every unit arrive by tcgen05.ld, per-unit constants are
+//              warp-uniform (kernel-parameter constant bank), the output head is a plain in-thread fp32 dot product,
+//              and reciprocals are shared between the r and z gates of a unit and the n gates of two units
+//              (4.5 MUFU per unit-step, gates.cuh).
+// Roles: 4 epilogue warps per tile (one per TMEM lane quarter) + 1 MMA-issue warp per tile; two tiles per CTA ping-pong
+// so one tile's MMA + hand-off latency hides behind the other tile's gate math.  mbarrier hand-off:
+//   epilogue: tcgen05.st (new A) -> wait::st -> fence::before_thread_sync -> arrive(h_ready[tile])      (count 4)
+//   issuer:   wait(h_ready) -> fence::after_thread_sync -> 5 x tcgen05.mma -> tcgen05.commit(acc_full[tile])
+// x is prefetched two steps ahead by the owning thread, y is written by the owning thread (partial sectors merge in L2).
+#include "gates.cuh"
+#include "tc_prims.cuh"
+
+namespace ntm {
+
+using namespace tc;
+
+namespace {
+
+constexpr int TS_M = 128;                  // streams per tile
+constexpr int TS_N = 192;                  // gate rows
+constexpr int TS_NK = 5;                   // MMAs along K = 64 + 16
+constexpr int TS_TILE_COLS = 256;          // TMEM columns reserved per tile: 192 accumulator + 40 operand (+ 24 spare)
+constexpr int TS_A_OFF = 192;              // first operand column inside a tile's TMEM block
+constexpr uint32_t TS_SBO = 128, TS_LBO = (TS_N / 8) * 128, TS_B_BYTES = 2 * TS_NK * TS_LBO;   // K-major, no swizzle
+constexpr uint32_t TS_OFF_BAR = TS_B_BYTES;
+constexpr uint32_t TS_SMEM_BYTES = TS_OFF_BAR + 64;
+constexpr int TS_UG = 8;                   // hidden units per TMEM load group
+
+template <int FMT>
+__device__ __forceinline__ uint32_t pack_op(float lo, float hi)
+{
+    if (FMT == FMT_BF16) return pack_bf16(lo, hi);
+    const __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+template <int FMT>
+__device__ __forceinline__ float round_op(float x)
+{
+    return FMT == FMT_BF16 ? __bfloat162float(__float2bfloat16_rn(x)) : __half2float(__float2half_rn(x));
+}
+
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&r)[4])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+                 "r"(r[2]), "r"(r[3])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st2(uint32_t taddr, uint32_t r0, uint32_t r1)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"(taddr), "r"(r0), "r"(r1) : "memory");
+}
+
+template <int FMT, int TILES>
+__global__ void __launch_bounds__(32 * 5 * TILES, 1) gru_tcs_kernel(const GruArgs a, const __grid_constant__ TcsConsts kc)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* const bop = smem;
+    uint64_t* const bars = reinterpret_cast<uint64_t*>(smem + TS_OFF_BAR);    // [tile]: h_ready, [TILES + tile]: acc_full
+    uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(smem + TS_OFF_BAR + 48);
+
+    const int tid = threadIdx.x;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int lane = tid & 31;
+    constexpr int EPI_WARPS = 4 * TILES;
+    constexpr uint32_t TMEM_COLS = TILES * TS_TILE_COLS;
+
+    // ---- one-time setup: TMEM, barriers, weights -> shared-memory B operand -----------------------------------
+    if (warp == EPI_WARPS) {
+        tmem_alloc(tmem_slot, TMEM_COLS);
+        tmem_relinquish();
+    }
+    if (tid == 0) {
+        for (int t = 0; t < TILES; ++t) {
+            mbar_init(&bars[t], 4);              // one arrive per epilogue warp of the tile
+            mbar_init(&bars[TILES + t], 1);      // tcgen05.commit
+        }
+        fence_mbar_init();
+    }
+    {
+        // image rows: [gate tile][row m (unit = m % 64)][80 k] 16-bit, k contiguous (pack_tc_images, gru_tc.cu); the B
+        // operand row n = gate * 64 + unit is K-major: 16-byte k chunks at LBO, 8-row groups at SBO
+        const uint4* img = reinterpret_cast<const uint4*>(a.blob + BlobLayout::tc_image(FMT));
+        for (int idx = tid; idx < TS_N * 2 * TS_NK; idx += blockDim.x) {
+            const int n = idx / (2 * TS_NK), c = idx % (2 * TS_NK);
+            const uint4 v = img[((n >> 6) * 128 + (n & 63)) * (2 * TS_NK) + c];
+            *reinterpret_cast<uint4*>(bop + c * TS_LBO + (n >> 3) * TS_SBO + (n & 7) * 16) = v;
+        }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp >= EPI_WARPS) {
+        // ================================ MMA issue warp of one tile ==========================================
+        const int tile = warp - EPI_WARPS;
+        const long long b0 = ((long long)blockIdx.x * TILES + tile) * TS_M;
+        if (b0 < a.B && elect_one()) {
+            constexpr uint32_t idesc = instr_desc(FMT, TS_M, TS_N);
+            const uint32_t d_base = tmem + (uint32_t)(tile * TS_TILE_COLS);
+            const uint32_t a_base = d_base + TS_A_OFF;
+            const uint32_t b_base = smem_u32(bop);
+            for (long long t = 0; t < a.T; ++t) {
+                mbar_wait(&bars[tile], (uint32_t)(t & 1));
+                tc_fence_after();
+#pragma unroll
+                for (int ks = 0; ks < TS_NK; ++ks)
+                    mma_ts<FMT>(d_base, a_base + ks * 8, smem_desc(b_base + ks * 2 * TS_LBO, TS_LBO, TS_SBO), idesc, ks > 0);
+                mma_commit(&bars[TILES + tile]);
+            }
+        }
+    } else {
+        // ================================ epilogue: one thread = one stream ====================================
+        const int tile = warp >> 2;
+        const int wq = warp & 3;                 // TMEM lane quarter (== warp id % 4)
+        const int s = wq * 32 + lane;            // stream inside the tile == TMEM lane
+        const long long b0 = ((long long)blockIdx.x * TILES + tile) * TS_M;
+        const int ns = (int)((a.B - b0) < (long long)TS_M ? (a.B - b0) : (long long)TS_M);   // may be <= 0
+        if (ns > 0) {
+            const bool valid = s < ns;
+            const long long row = b0 + (valid ? s : 0);
+            const float* __restrict__ xp = a.x + row * a.ldx;
+            float* __restrict__ yp = a.y + row * a.ldy;
+            const uint32_t t_acc = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(tile * TS_TILE_COLS);
+            const uint32_t t_op = t_acc + TS_A_OFF;
+
+            // ---- initial state: fp32 in registers, rounded copy + the first input sample into the A operand ----
+            float h[64];
+#pragma unroll
+            for (int j = 0; j < 64; ++j) h[j] = (valid && a.h_in) ? a.h_in[row * 64 + j] : 0.0f;
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+                uint32_t w[4];
+#pragma unroll
+                for (int p = 0; p < 4; ++p) w[p] = pack_op<FMT>(h[8 * g + 2 * p], h[8 * g + 2 * p + 1]);
+                tmem_st4(t_op + 4 * g, w);
+            }
+            float x0 = valid ? xp[0] : 0.0f;
+            float x1 = (valid && a.T > 1) ? xp[1] : 0.0f;
+            {
+                // K augmentation, columns 32..39 = k 64..79: [x_hi, x_lo | x_hi, 1 | 1, 0 | 0 ...]
+                const float xh = round_op<FMT>(x0);
+                const uint32_t w[4] = {pack_op<FMT>(1.0f, 0.0f), 0u, 0u, 0u};
+                tmem_st2(t_op + 32, pack_op<FMT>(xh, x0 - xh), pack_op<FMT>(xh, 1.0f));
+                tmem_st4(t_op + 34, w);
+                tmem_st2(t_op + 38, 0u, 0u);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars[tile]);
+
+            for (long long t = 0; t < a.T; ++t) {
+                const float x2 = (valid && t + 2 < a.T) ? __ldg(xp + t + 2) : 0.0f;
+                mbar_wait(&bars[TILES + tile], (uint32_t)(t & 1));
+                tc_fence_after();
+
+                float ys[4] = {kc.bo, 0.0f, 0.0f, 0.0f};
+                uint32_t acc[2][3][TS_UG];
+                tmem_ld8(t_acc + 0, acc[0][0]);
+                tmem_ld8(t_acc + 64, acc[0][1]);
+                tmem_ld8(t_acc + 128, acc[0][2]);
+#pragma unroll
+                for (int g = 0; g < 64 / TS_UG; ++g) {
+                    tmem_ld_wait();
+                    if (g + 1 < 64 / TS_UG) {
+                        tmem_ld8(t_acc + (g + 1) * TS_UG, acc[(g + 1) & 1][0]);
+                        tmem_ld8(t_acc + 64 + (g + 1) * TS_UG, acc[(g + 1) & 1][1]);
+                        tmem_ld8(t_acc + 128 + (g + 1) * TS_UG, acc[(g + 1) & 1][2]);
+                    }
+                    const uint32_t(&ar)[TS_UG] = acc[g & 1][0];
+                    const uint32_t(&az)[TS_UG] = acc[g & 1][1];
+                    const uint32_t(&an)[TS_UG] = acc[g & 1][2];
+                    uint32_t w[TS_UG / 2];
+#pragma unroll
+                    for (int p = 0; p < TS_UG / 2; ++p) {
+                        const int j = g * TS_UG + 2 * p;
+                        float z0, dn0, z1, dn1, hn0, hn1;
+                        // accumulators hold the complete scaled pre-activations of r, z and W_hn h + b_hn
+                        gates_rz_dn_pre(__uint_as_float(ar[2 * p]), __uint_as_float(az[2 * p]), __uint_as_float(an[2 * p]),
+                                        fmaf(kc.cn_w[j], x0, kc.cn_b[j]), z0, dn0);
+                        gates_rz_dn_pre(__uint_as_float(ar[2 * p + 1]), __uint_as_float(az[2 * p + 1]),
+                                        __uint_as_float(an[2 * p + 1]), fmaf(kc.cn_w[j + 1], x0, kc.cn_b[j + 1]), z1, dn1);
+                        gates_blend2(z0, dn0, h[j], z1, dn1, h[j + 1], hn0, hn1);
+                        h[j] = hn0;
+                        h[j + 1] = hn1;
+                        ys[p & 3] = fmaf(kc.wo[j], hn0, ys[p & 3]);
+                        ys[(p + 2) & 3] = fmaf(kc.wo[j + 1], hn1, ys[(p + 2) & 3]);
+                        w[p] = pack_op<FMT>(hn0, hn1);
+                    }
+                    tmem_st4(t_op + g * (TS_UG / 2), w);
+                }
+                {
+                    const float xh = round_op<FMT>(x1);      // input sample of the NEXT step
+                    tmem_st2(t_op + 32, pack_op<FMT>(xh, x1 - xh), pack_op<FMT>(xh, 1.0f));
+                }
+                // release the next MMA batch of this tile
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars[tile]);
+
+                float v = (ys[0] + ys[1]) + (ys[2] + ys[3]);
+                if (a.skip) v += x0;
+                if (valid) yp[t] = v;
+                x0 = x1;
+                x1 = x2;
+            }
+
+            if (valid) {
+#pragma unroll
+                for (int j = 0; j < 64; ++j) a.h_out[row * 64 + j] = h[j];
+            }
+        }
+    }
+
+    // ---- teardown: every MMA has completed (the epilogue consumed the last accumulator) ------------------------
+    tc_fence_before();
+    __syncthreads();
+    if (warp == EPI_WARPS) tmem_dealloc(tmem, TMEM_COLS);
+}
+
+template <int FMT, int TILES>
+cudaError_t launch_tcs_one(const GruArgs& a, const TcsConsts& kc, cudaStream_t st)
+{
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 64 && !configured[dev]) {
+        e = cudaFuncSetAttribute(gru_tcs_kernel<FMT, TILES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)TS_SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        configured[dev] = true;
+    }
+    const long long per_cta = (long long)TS_M * TILES;
+    const long long grid = (a.B + per_cta - 1) / per_cta;
+    gru_tcs_kernel<FMT, TILES><<<(unsigned)grid, 32 * 5 * TILES, TS_SMEM_BYTES, st>>>(a, kc);
+    ++g_launches;
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+// host: the warp-uniform per-unit constants of the stream-major kernel, from the fp32 part of the blob
+void fill_tcs_consts(const float* blob_host, TcsConsts* kc)
+{
+    constexpr float L = 1.4426950408889634f;
+    for (int j = 0; j < 64; ++j) {
+        kc->cn_w[j] = 2.0f * L * blob_host[BlobLayout::W_IH + 128 + j];
+        kc->cn_b[j] = 2.0f * L * blob_host[BlobLayout::B_IH + 128 + j];
+        kc->wo[j] = blob_host[BlobLayout::W_OUT + j];
+    }
+    kc->bo = blob_host[BlobLayout::B_OUT];
+}
+
+// fmt: FMT_F16 / FMT_BF16.  tiles: 128-stream tiles per CTA (1 or 2; 0 = automatic).  Plain GRU only (a.d == nullptr).
+cudaError_t launch_gru_tcs(const GruArgs& a, const TcsConsts& kc, int fmt, int sm_count, int tiles, cudaStream_t st)
+{
+    if (a.B <= 0 || a.T <= 0) return cudaSuccess;
+    if (a.d != nullptr) return cudaErrorInvalidValue;
+    if (tiles <= 0) tiles = a.B > (long long)sm_count * TS_M ? 2 : 1;
+    if (fmt == FMT_BF16) return tiles >= 2 ? launch_tcs_one<FMT_BF16, 2>(a, kc, st) : launch_tcs_one<FMT_BF16, 1>(a, kc, st);
+    return tiles >= 2 ? launch_tcs_one<FMT_F16, 2>(a, kc, st) : launch_tcs_one<FMT_F16, 1>(a, kc, st);
+}
+
+}  // namespace ntm

@@ -43,9 +43,20 @@ struct GruArgs {
     int skip;
 };
 
+// Warp-uniform per-unit constants of the stream-major tcgen05 kernel (gru_tcs.cu); passed as a kernel parameter so
+// that they are constant-bank operands.  Scaled like the n-gate rows (2 log2 e).
+struct TcsConsts {
+    float cn_w[64];   // W_in
+    float cn_b[64];   // b_in
+    float wo[64];     // output head
+    float bo;
+};
+
 // per-TU launchers -------------------------------------------------------------------------------
 cudaError_t launch_gru_fp32(const GruArgs& a, int sm_count, int tune_s, int tune_ks, int fast_act, cudaStream_t st);
 cudaError_t launch_gru_tc(const GruArgs& a, int fmt, int sm_count, int tune_n, int tune_g, cudaStream_t st);
+cudaError_t launch_gru_tcs(const GruArgs& a, const TcsConsts& kc, int fmt, int sm_count, int tiles, cudaStream_t st);
+void fill_tcs_consts(const float* blob_host, TcsConsts* kc);
 cudaError_t launch_gru_mma(const GruArgs& a, int fmt, int n_tiles, cudaStream_t st);
 void pack_tc_images(float* blob_host);   // host: fills BlobLayout::IMG_* from the fp32 part of the blob
 cudaError_t launch_delay(const float* x, long long ldx, const float* d, long long ldd, float* y, long long ldy,
