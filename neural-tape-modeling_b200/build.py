@@ -13,7 +13,8 @@ LIB = os.path.join(PKG, "libntm_b200.so")
 OBJ = os.path.join(PKG, "build")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hidden", "-Xptxas", "-v"]
+EXTRA = os.environ.get("NTM_EXTRA_NVCC_FLAGS", "").split()
+FLAGS = [*EXTRA, "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hidden", "-Xptxas", "-v"]
 
 
 def _sources():

@@ -17,7 +17,7 @@ thread_local int t_last_cuda = 0;
 int g_tune_s = 0, g_tune_ks = 0, g_tune_fast = 0;
 // 0 fp32 CUDA-core, 1 warp-level mma.sync, 2 tcgen05 weight-stationary, 3 tcgen05 stream-major (NTM_Q_LAST_KERNEL)
 int g_last_kernel = -1;
-long long g_tcs_min_streams_per_sm = 128;     // crossover mma.sync -> stream-major tcgen05 kernel
+long long g_tcs_min_streams_per_sm = 110;     // crossover mma.sync -> stream-major tcgen05 kernel
 
 struct HostPipe {            // staging of the *_host entry points
     cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
@@ -79,13 +79,13 @@ int run_gru(Handle* hd, int mode, const ntm::GruArgs& a, cudaStream_t st)
         // latency regime (few streams per SM): warp-level mma.sync kernel; throughput regime (>= one 128-stream tile
         // per SM, plain GRU, 16-bit operands): stream-major tcgen05 kernel.
         // ntm_set_tuning(n, 3) forces mma.sync with n/8 tiles per CTA, (n, 1|2) the weight-stationary tcgen05 kernel,
-        // (tiles, 4) the stream-major tcgen05 kernel with 1 or 2 tiles per CTA.
+        // (tiles + 4 * (variant + 1), 4) the stream-major tcgen05 kernel with 1 or 2 tiles per CTA (variant: experiments).
         const int tg = g_tune_ks & 0xff;
         const bool tcs_ok = fmt != 2 && a.d == nullptr;     // (tf32 operands exist only in the mma.sync kernel)
         const bool use_tcs = tcs_ok && (tg == 4 || (tg == 0 && a.B >= (long long)hd->sm_count * g_tcs_min_streams_per_sm));
         const bool use_mma = !use_tcs && (tg == 3 || tg == 4 || tg == 0 || fmt == 2);
         if (use_tcs) {
-            CU(ntm::launch_gru_tcs(a, hd->tcs, fmt, hd->sm_count, tg == 4 ? g_tune_s : 0, st));
+            CU(ntm::launch_gru_tcs(a, hd->tcs, fmt, hd->sm_count, tg == 4 ? (g_tune_s & 3) : 0, tg == 4 ? (g_tune_s >> 2) - 1 : -1, st));
             g_last_kernel = 3;
         } else if (use_mma) {
             const int nt = g_tune_s > 0 && tg == 3 ? g_tune_s / 8 : 1;

@@ -68,6 +68,55 @@ __device__ __forceinline__ void gates_blend2(float z0, float dn0, float h0, floa
     hn1 = fmaf(z1, h1 - n1, n1);
 }
 
+// 2^x on the FMA/ALU pipes (no MUFU): round-to-nearest split x = i + f, f in [-0.5, 0.5], degree-5 minimax polynomial
+// (max relative error 2.4e-7 in fp32 Horner form = the accuracy class of ex2.approx), exponent inserted by an integer
+// add.  x must be <= 127 on entry (callers clamp to EX2_CLAMP); clamped below at -125 (result ~2^-125 instead of 0).
+__device__ __forceinline__ float ex2_poly(float x)
+{
+    x = fmaxf(x, -125.0f);
+    const float t = x + 12582912.0f;                 // 1.5 * 2^23: the integer part lands in the low mantissa bits
+    const float f = x - (t - 12582912.0f);
+    float p = 1.327647129e-03f;
+    p = fmaf(p, f, 9.675540961e-03f);
+    p = fmaf(p, f, 5.550713092e-02f);
+    p = fmaf(p, f, 2.402212024e-01f);
+    p = fmaf(p, f, 6.931469440e-01f);
+    p = fmaf(p, f, 1.000000119e+00f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
+// Two hidden units (0, 1) of ONE stream, complete pre-activations (see gates_rz_dn_pre), new states out.
+//   SHARE4: one reciprocal serves r and z of BOTH units (4.0 MUFU per unit-step instead of 4.5); the ex2 arguments of
+//           r, z are then clamped to 30 so that the product of four denominators stays below 2^121 (sigmoid saturates
+//           at 2^-30 instead of 2^-60: absolute error < 1e-9).
+//   NPOLY:  how many of the six ex2 of the two units run on the FMA pipe (ex2_poly) instead of MUFU: 0, 1 (z of unit 1)
+//           or 2 (z of both units) -- the z gates are off the r -> n dependency chain.
+template <bool SHARE4, int NPOLY>
+__device__ __forceinline__ void gates_unit_pair(float ar0, float az0, float an0, float gin0, float ar1, float az1, float an1,
+                                                float gin1, float h0, float h1, float& hn0, float& hn1)
+{
+    constexpr float C = SHARE4 ? 30.0f : EX2_CLAMP;
+    const float dr0 = 1.0f + ex2_approx(fminf(ar0, C));
+    const float dr1 = 1.0f + ex2_approx(fminf(ar1, C));
+    const float dz0 = 1.0f + (NPOLY >= 2 ? ex2_poly(fminf(az0, C)) : ex2_approx(fminf(az0, C)));
+    const float dz1 = 1.0f + (NPOLY >= 1 ? ex2_poly(fminf(az1, C)) : ex2_approx(fminf(az1, C)));
+    float r0, z0, r1, z1;
+    if (SHARE4) {
+        const float p0 = dr0 * dz0, p1 = dr1 * dz1;
+        const float q = rcp_approx(p0 * p1);
+        const float i0 = p1 * q, i1 = p0 * q;
+        r0 = dz0 * i0; z0 = dr0 * i0;
+        r1 = dz1 * i1; z1 = dr1 * i1;
+    } else {
+        const float i0 = rcp_approx(dr0 * dz0), i1 = rcp_approx(dr1 * dz1);
+        r0 = dz0 * i0; z0 = dr0 * i0;
+        r1 = dz1 * i1; z1 = dr1 * i1;
+    }
+    const float dn0 = 1.0f + ex2_approx(fminf(fmaf(r0, an0, gin0), EX2_CLAMP));
+    const float dn1 = 1.0f + ex2_approx(fminf(fmaf(r1, an1, gin1), EX2_CLAMP));
+    gates_blend2(z0, dn0, h0, z1, dn1, h1, hn0, hn1);
+}
+
 // new state of one pair (own reciprocal: keeps a stream's arithmetic independent of its neighbours)
 __device__ __forceinline__ float gates_blend1(float z, float dn, float h)
 {

@@ -39,9 +39,24 @@ constexpr int TS_NK = 5;                   // MMAs along K = 64 + 16
 constexpr int TS_TILE_COLS = 256;          // TMEM columns reserved per tile: 192 accumulator + 40 operand (+ 24 spare)
 constexpr int TS_A_OFF = 192;              // first operand column inside a tile's TMEM block
 constexpr uint32_t TS_SBO = 128, TS_LBO = (TS_N / 8) * 128, TS_B_BYTES = 2 * TS_NK * TS_LBO;   // K-major, no swizzle
-constexpr uint32_t TS_OFF_BAR = TS_B_BYTES;
-constexpr uint32_t TS_SMEM_BYTES = TS_OFF_BAR + 64;
+constexpr uint32_t TS_OFF_BAR = TS_B_BYTES;                       // 6 mbarriers + the TMEM base slot
+constexpr uint32_t TS_OFF_YP = TS_OFF_BAR + 64;                   // [2 tiles][2][128] floats
+constexpr uint32_t TS_SMEM_BYTES = TS_OFF_YP + 2 * 2 * 128 * 4;
 constexpr int TS_UG = 8;                   // hidden units per TMEM load group
+constexpr int TCS_DEFAULT_UW = 2;           // two threads per stream (measured best)
+constexpr int TCS_DEFAULT_VAR = 3;          // staggered tiles + reciprocal shared by two units
+
+#ifdef NTM_TCS_TRACE
+// debug build only (NTM_EXTRA_NVCC_FLAGS=-DNTM_TCS_TRACE): per-step clock stamps of CTA 0, [tile][step][start, mid, end]
+__device__ long long g_tcs_trace[2 * 256 * 3];
+#define TCS_STAMP(slot)                                                                          \
+    do {                                                                                         \
+        if (blockIdx.x == 0 && lane == 0 && wq == 0 && uh == 0 && t >= 64 && t < 64 + 256)       \
+            g_tcs_trace[(tile * 256 + (int)(t - 64)) * 3 + (slot)] = clock64();                  \
+    } while (0)
+#else
+#define TCS_STAMP(slot) do {} while (0)
+#endif
 
 template <int FMT>
 __device__ __forceinline__ uint32_t pack_op(float lo, float hi)
@@ -67,18 +82,179 @@ __device__ __forceinline__ void tmem_st2(uint32_t taddr, uint32_t r0, uint32_t r
     asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"(taddr), "r"(r0), "r"(r1) : "memory");
 }
 
-template <int FMT, int TILES>
-__global__ void __launch_bounds__(32 * 5 * TILES, 1) gru_tcs_kernel(const GruArgs a, const __grid_constant__ TcsConsts kc)
+// Gate math of one tile: one thread = one stream (UW == 1) or one NU-unit slice of it (UW == 2, slice UH).
+template <int FMT, int TILES, int UW, int VAR, int UH>
+__device__ __forceinline__ void tcs_epilogue(const GruArgs& a, const TcsConsts& kc, int tile, int wq, int lane, uint32_t tmem,
+                                             uint64_t* bars, float* ypart)
+{
+    constexpr bool STAGGER = (VAR & 1) != 0 && TILES == 2, SHARE4 = (VAR & 2) != 0;
+    constexpr int NPOLY = (VAR >> 2) & 3;
+    constexpr int NU = 64 / UW;                  // hidden units per thread
+    constexpr int NG = NU / TS_UG;               // TMEM load groups per thread and step
+    constexpr bool PREFETCH = UW == 1;           // double-buffered accumulator loads (registers allow it only for UW == 1)
+    constexpr int uh = UH, u0 = UH * NU;
+    const int s = wq * 32 + lane;            // stream inside the tile == TMEM lane
+    const long long b0 = ((long long)blockIdx.x * TILES + tile) * TS_M;
+    const int ns = (int)((a.B - b0) < (long long)TS_M ? (a.B - b0) : (long long)TS_M);   // may be <= 0
+    // both tiles of the CTA are live (the stagger protocol needs a partner)
+    const bool stagger = STAGGER && ((long long)blockIdx.x * TILES + 1) * TS_M < a.B;
+    if (ns > 0) {
+        const bool valid = s < ns;
+        const long long row = b0 + (valid ? s : 0);
+        const float* __restrict__ xp = a.x + row * a.ldx;
+        float* __restrict__ yp = a.y + row * a.ldy;
+        const uint32_t t_acc = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(tile * TS_TILE_COLS);
+        const uint32_t t_op = t_acc + TS_A_OFF;
+        float* const yslot = ypart + tile * 2 * TS_M + s;
+
+        // ---- initial state: fp32 in registers, rounded copy + the first input sample into the A operand ----
+        float h[NU];
+#pragma unroll
+        for (int j = 0; j < NU; ++j) h[j] = (valid && a.h_in) ? a.h_in[row * 64 + u0 + j] : 0.0f;
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+            uint32_t w[4];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) w[p] = pack_op<FMT>(h[8 * g + 2 * p], h[8 * g + 2 * p + 1]);
+            tmem_st4(t_op + u0 / 2 + 4 * g, w);
+        }
+        float x0 = valid ? xp[0] : 0.0f;
+        float x1 = (valid && a.T > 1) ? xp[1] : 0.0f;
+        float xprev = 0.0f, yprev = 0.0f;    // UW == 2: this thread's head partial / input sample of the previous step
+        if (uh == 0) {
+            // K augmentation, columns 32..39 = k 64..79: [x_hi, x_lo | x_hi, 1 | 1, 0 | 0 ...]
+            const float xh = round_op<FMT>(x0);
+            const uint32_t w[4] = {pack_op<FMT>(1.0f, 0.0f), 0u, 0u, 0u};
+            tmem_st2(t_op + 32, pack_op<FMT>(xh, x0 - xh), pack_op<FMT>(xh, 1.0f));
+            tmem_st4(t_op + 34, w);
+            tmem_st2(t_op + 38, 0u, 0u);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[tile]);
+
+        for (long long t = 0; t < a.T; ++t) {
+            const float x2 = (valid && t + 2 < a.T) ? __ldg(xp + t + 2) : 0.0f;
+            if (stagger && (tile == 1 || t > 0)) mbar_wait_sleep(&bars[4 + (tile ^ 1)], (uint32_t)((t - (tile == 0)) & 1));
+            mbar_wait_sleep(&bars[2 + tile], (uint32_t)(t & 1));
+            tc_fence_after();
+            TCS_STAMP(0);
+            if (UW == 2 && uh == 0 && t > 0) {
+                // the partner's head partial of the previous step (published before its h_ready arrive, which
+                // happens-before the commit this thread just observed)
+                float v = yprev + yslot[((t - 1) & 1) * TS_M];
+                if (a.skip) v += xprev;
+                if (valid) yp[t - 1] = v;
+            }
+
+            float ys[4] = {uh == 0 ? kc.bo : 0.0f, 0.0f, 0.0f, 0.0f};
+            uint32_t acc[PREFETCH ? 2 : 1][3][TS_UG];
+            tmem_ld8(t_acc + u0, acc[0][0]);
+            tmem_ld8(t_acc + 64 + u0, acc[0][1]);
+            tmem_ld8(t_acc + 128 + u0, acc[0][2]);
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+                constexpr int NB = PREFETCH ? 2 : 1;
+                tmem_ld_wait();
+                if (PREFETCH && g + 1 < NG) {
+                    tmem_ld8(t_acc + u0 + (g + 1) * TS_UG, acc[(g + 1) % NB][0]);
+                    tmem_ld8(t_acc + 64 + u0 + (g + 1) * TS_UG, acc[(g + 1) % NB][1]);
+                    tmem_ld8(t_acc + 128 + u0 + (g + 1) * TS_UG, acc[(g + 1) % NB][2]);
+                }
+                float pre[3][TS_UG];
+#pragma unroll
+                for (int i = 0; i < TS_UG; ++i) {
+                    pre[0][i] = __uint_as_float(acc[g % NB][0][i]);
+                    pre[1][i] = __uint_as_float(acc[g % NB][1][i]);
+                    pre[2][i] = __uint_as_float(acc[g % NB][2][i]);
+                }
+                if (!PREFETCH && g + 1 < NG) {       // the registers are free again: next group's loads fly during the math
+                    tmem_ld8(t_acc + u0 + (g + 1) * TS_UG, acc[0][0]);
+                    tmem_ld8(t_acc + 64 + u0 + (g + 1) * TS_UG, acc[0][1]);
+                    tmem_ld8(t_acc + 128 + u0 + (g + 1) * TS_UG, acc[0][2]);
+                }
+                uint32_t w[TS_UG / 2];
+#pragma unroll
+                for (int p = 0; p < TS_UG / 2; ++p) {
+                    const int jl = g * TS_UG + 2 * p, j = u0 + jl;       // local / global unit index (j static per uh)
+                    float hn0, hn1;
+                    // accumulators hold the complete scaled pre-activations of r, z and W_hn h + b_hn
+                    const float g0 = fmaf(kc.cn_w[j], x0, kc.cn_b[j]);
+                    const float g1 = fmaf(kc.cn_w[j + 1], x0, kc.cn_b[j + 1]);
+                    gates_unit_pair<SHARE4, NPOLY>(pre[0][2 * p], pre[1][2 * p], pre[2][2 * p], g0, pre[0][2 * p + 1],
+                                                   pre[1][2 * p + 1], pre[2][2 * p + 1], g1, h[jl], h[jl + 1], hn0, hn1);
+                    h[jl] = hn0;
+                    h[jl + 1] = hn1;
+                    const float w0 = kc.wo[j];
+                    const float w1 = kc.wo[j + 1];
+                    ys[p & 3] = fmaf(w0, hn0, ys[p & 3]);
+                    ys[(p + 2) & 3] = fmaf(w1, hn1, ys[(p + 2) & 3]);
+                    w[p] = pack_op<FMT>(hn0, hn1);
+                }
+                tmem_st4(t_op + u0 / 2 + g * (TS_UG / 2), w);
+                if (g == NG / 2 - 1) TCS_STAMP(1);
+                if (stagger && g == NG / 2 - 1) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars[4 + tile]);
+                }
+            }
+            if (uh == 0) {
+                const float xh = round_op<FMT>(x1);      // input sample of the NEXT step
+                tmem_st2(t_op + 32, pack_op<FMT>(xh, x1 - xh), pack_op<FMT>(xh, 1.0f));
+            }
+            float v = (ys[0] + ys[1]) + (ys[2] + ys[3]);
+            if (UW == 2 && uh == 1) yslot[(t & 1) * TS_M] = v;
+            // release the next MMA batch of this tile
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars[tile]);
+            TCS_STAMP(2);
+
+            if (UW == 1) {
+                if (a.skip) v += x0;
+                if (valid) yp[t] = v;
+            } else {
+                yprev = v;                   // uh == 0: completed by the partner's partial at the next step
+                xprev = x0;
+            }
+            x0 = x1;
+            x1 = x2;
+        }
+        if (UW == 2) {
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + tile), "r"(64 * 4) : "memory");     // last partials visible
+            if (uh == 0 && valid) {
+                float v = yprev + yslot[((a.T - 1) & 1) * TS_M];
+                if (a.skip) v += xprev;
+                yp[a.T - 1] = v;
+            }
+        }
+
+        if (valid) {
+#pragma unroll
+            for (int j = 0; j < NU; ++j) a.h_out[row * 64 + u0 + j] = h[j];
+        }
+    }
+}
+
+// UW: epilogue warps per TMEM lane quarter (1: a thread owns all 64 units of its stream; 2: two threads own 32 units each).
+// VAR bit 0: staggered tiles (a tile may start a step's gate math only after the other tile passed the middle of its
+//            own -- keeps the two tiles of a CTA in anti-phase); bit 1: reciprocal shared by two
+//            units (4.0 MUFU per unit-step); bits 2-3: ex2 evaluations per unit pair moved to the FMA pipe.
+template <int FMT, int TILES, int UW, int VAR>
+__global__ void __launch_bounds__(32 * (4 * UW + 1) * TILES, 1) gru_tcs_kernel(const GruArgs a, const __grid_constant__ TcsConsts kc)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* const bop = smem;
-    uint64_t* const bars = reinterpret_cast<uint64_t*>(smem + TS_OFF_BAR);    // [tile]: h_ready, [TILES + tile]: acc_full
-    uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(smem + TS_OFF_BAR + 48);
+    uint64_t* const bars = reinterpret_cast<uint64_t*>(smem + TS_OFF_BAR);    // [tile]: h_ready, [2 + tile]: acc_full, [4 + tile]: mid
+    uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(smem + TS_OFF_BAR + 56);
+    float* const ypart = reinterpret_cast<float*>(smem + TS_OFF_YP);          // [tile][2][128] head partials (UW == 2)
 
     const int tid = threadIdx.x;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int lane = tid & 31;
-    constexpr int EPI_WARPS = 4 * TILES;
+    constexpr int EPI_WARPS = 4 * UW * TILES;
     constexpr uint32_t TMEM_COLS = TILES * TS_TILE_COLS;
 
     // ---- one-time setup: TMEM, barriers, weights -> shared-memory B operand -----------------------------------
@@ -88,8 +264,9 @@ __global__ void __launch_bounds__(32 * 5 * TILES, 1) gru_tcs_kernel(const GruArg
     }
     if (tid == 0) {
         for (int t = 0; t < TILES; ++t) {
-            mbar_init(&bars[t], 4);              // one arrive per epilogue warp of the tile
-            mbar_init(&bars[TILES + t], 1);      // tcgen05.commit
+            mbar_init(&bars[t], 4 * UW);         // one arrive per epilogue warp of the tile
+            mbar_init(&bars[2 + t], 1);          // tcgen05.commit
+            mbar_init(&bars[4 + t], 4 * UW);     // middle of the tile's gate math
         }
         fence_mbar_init();
     }
@@ -119,117 +296,20 @@ __global__ void __launch_bounds__(32 * 5 * TILES, 1) gru_tcs_kernel(const GruArg
             const uint32_t a_base = d_base + TS_A_OFF;
             const uint32_t b_base = smem_u32(bop);
             for (long long t = 0; t < a.T; ++t) {
-                mbar_wait(&bars[tile], (uint32_t)(t & 1));
+                mbar_wait_sleep(&bars[tile], (uint32_t)(t & 1));
                 tc_fence_after();
 #pragma unroll
                 for (int ks = 0; ks < TS_NK; ++ks)
                     mma_ts<FMT>(d_base, a_base + ks * 8, smem_desc(b_base + ks * 2 * TS_LBO, TS_LBO, TS_SBO), idesc, ks > 0);
-                mma_commit(&bars[TILES + tile]);
+                mma_commit(&bars[2 + tile]);
             }
         }
     } else {
-        // ================================ epilogue: one thread = one stream ====================================
-        const int tile = warp >> 2;
+        // ================================ epilogue warps ===========================================================
+        const int tile = warp / (4 * UW);
         const int wq = warp & 3;                 // TMEM lane quarter (== warp id % 4)
-        const int s = wq * 32 + lane;            // stream inside the tile == TMEM lane
-        const long long b0 = ((long long)blockIdx.x * TILES + tile) * TS_M;
-        const int ns = (int)((a.B - b0) < (long long)TS_M ? (a.B - b0) : (long long)TS_M);   // may be <= 0
-        if (ns > 0) {
-            const bool valid = s < ns;
-            const long long row = b0 + (valid ? s : 0);
-            const float* __restrict__ xp = a.x + row * a.ldx;
-            float* __restrict__ yp = a.y + row * a.ldy;
-            const uint32_t t_acc = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(tile * TS_TILE_COLS);
-            const uint32_t t_op = t_acc + TS_A_OFF;
-
-            // ---- initial state: fp32 in registers, rounded copy + the first input sample into the A operand ----
-            float h[64];
-#pragma unroll
-            for (int j = 0; j < 64; ++j) h[j] = (valid && a.h_in) ? a.h_in[row * 64 + j] : 0.0f;
-#pragma unroll
-            for (int g = 0; g < 8; ++g) {
-                uint32_t w[4];
-#pragma unroll
-                for (int p = 0; p < 4; ++p) w[p] = pack_op<FMT>(h[8 * g + 2 * p], h[8 * g + 2 * p + 1]);
-                tmem_st4(t_op + 4 * g, w);
-            }
-            float x0 = valid ? xp[0] : 0.0f;
-            float x1 = (valid && a.T > 1) ? xp[1] : 0.0f;
-            {
-                // K augmentation, columns 32..39 = k 64..79: [x_hi, x_lo | x_hi, 1 | 1, 0 | 0 ...]
-                const float xh = round_op<FMT>(x0);
-                const uint32_t w[4] = {pack_op<FMT>(1.0f, 0.0f), 0u, 0u, 0u};
-                tmem_st2(t_op + 32, pack_op<FMT>(xh, x0 - xh), pack_op<FMT>(xh, 1.0f));
-                tmem_st4(t_op + 34, w);
-                tmem_st2(t_op + 38, 0u, 0u);
-            }
-            tmem_st_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bars[tile]);
-
-            for (long long t = 0; t < a.T; ++t) {
-                const float x2 = (valid && t + 2 < a.T) ? __ldg(xp + t + 2) : 0.0f;
-                mbar_wait(&bars[TILES + tile], (uint32_t)(t & 1));
-                tc_fence_after();
-
-                float ys[4] = {kc.bo, 0.0f, 0.0f, 0.0f};
-                uint32_t acc[2][3][TS_UG];
-                tmem_ld8(t_acc + 0, acc[0][0]);
-                tmem_ld8(t_acc + 64, acc[0][1]);
-                tmem_ld8(t_acc + 128, acc[0][2]);
-#pragma unroll
-                for (int g = 0; g < 64 / TS_UG; ++g) {
-                    tmem_ld_wait();
-                    if (g + 1 < 64 / TS_UG) {
-                        tmem_ld8(t_acc + (g + 1) * TS_UG, acc[(g + 1) & 1][0]);
-                        tmem_ld8(t_acc + 64 + (g + 1) * TS_UG, acc[(g + 1) & 1][1]);
-                        tmem_ld8(t_acc + 128 + (g + 1) * TS_UG, acc[(g + 1) & 1][2]);
-                    }
-                    const uint32_t(&ar)[TS_UG] = acc[g & 1][0];
-                    const uint32_t(&az)[TS_UG] = acc[g & 1][1];
-                    const uint32_t(&an)[TS_UG] = acc[g & 1][2];
-                    uint32_t w[TS_UG / 2];
-#pragma unroll
-                    for (int p = 0; p < TS_UG / 2; ++p) {
-                        const int j = g * TS_UG + 2 * p;
-                        float z0, dn0, z1, dn1, hn0, hn1;
-                        // accumulators hold the complete scaled pre-activations of r, z and W_hn h + b_hn
-                        gates_rz_dn_pre(__uint_as_float(ar[2 * p]), __uint_as_float(az[2 * p]), __uint_as_float(an[2 * p]),
-                                        fmaf(kc.cn_w[j], x0, kc.cn_b[j]), z0, dn0);
-                        gates_rz_dn_pre(__uint_as_float(ar[2 * p + 1]), __uint_as_float(az[2 * p + 1]),
-                                        __uint_as_float(an[2 * p + 1]), fmaf(kc.cn_w[j + 1], x0, kc.cn_b[j + 1]), z1, dn1);
-                        gates_blend2(z0, dn0, h[j], z1, dn1, h[j + 1], hn0, hn1);
-                        h[j] = hn0;
-                        h[j + 1] = hn1;
-                        ys[p & 3] = fmaf(kc.wo[j], hn0, ys[p & 3]);
-                        ys[(p + 2) & 3] = fmaf(kc.wo[j + 1], hn1, ys[(p + 2) & 3]);
-                        w[p] = pack_op<FMT>(hn0, hn1);
-                    }
-                    tmem_st4(t_op + g * (TS_UG / 2), w);
-                }
-                {
-                    const float xh = round_op<FMT>(x1);      // input sample of the NEXT step
-                    tmem_st2(t_op + 32, pack_op<FMT>(xh, x1 - xh), pack_op<FMT>(xh, 1.0f));
-                }
-                // release the next MMA batch of this tile
-                tmem_st_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bars[tile]);
-
-                float v = (ys[0] + ys[1]) + (ys[2] + ys[3]);
-                if (a.skip) v += x0;
-                if (valid) yp[t] = v;
-                x0 = x1;
-                x1 = x2;
-            }
-
-            if (valid) {
-#pragma unroll
-                for (int j = 0; j < 64; ++j) a.h_out[row * 64 + j] = h[j];
-            }
-        }
+        if (UW == 1 || ((warp >> 2) & 1) == 0) tcs_epilogue<FMT, TILES, UW, VAR, 0>(a, kc, tile, wq, lane, tmem, bars, ypart);
+        else tcs_epilogue<FMT, TILES, UW, VAR, UW - 1>(a, kc, tile, wq, lane, tmem, bars, ypart);
     }
 
     // ---- teardown: every MMA has completed (the epilogue consumed the last accumulator) ------------------------
@@ -238,7 +318,7 @@ __global__ void __launch_bounds__(32 * 5 * TILES, 1) gru_tcs_kernel(const GruArg
     if (warp == EPI_WARPS) tmem_dealloc(tmem, TMEM_COLS);
 }
 
-template <int FMT, int TILES>
+template <int FMT, int TILES, int UW, int VAR>
 cudaError_t launch_tcs_one(const GruArgs& a, const TcsConsts& kc, cudaStream_t st)
 {
     static bool configured[64] = {};
@@ -246,19 +326,26 @@ cudaError_t launch_tcs_one(const GruArgs& a, const TcsConsts& kc, cudaStream_t s
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     if (dev < 64 && !configured[dev]) {
-        e = cudaFuncSetAttribute(gru_tcs_kernel<FMT, TILES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        e = cudaFuncSetAttribute(gru_tcs_kernel<FMT, TILES, UW, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)TS_SMEM_BYTES);
         if (e != cudaSuccess) return e;
         configured[dev] = true;
     }
     const long long per_cta = (long long)TS_M * TILES;
     const long long grid = (a.B + per_cta - 1) / per_cta;
-    gru_tcs_kernel<FMT, TILES><<<(unsigned)grid, 32 * 5 * TILES, TS_SMEM_BYTES, st>>>(a, kc);
+    gru_tcs_kernel<FMT, TILES, UW, VAR><<<(unsigned)grid, 32 * (4 * UW + 1) * TILES, TS_SMEM_BYTES, st>>>(a, kc);
     ++g_launches;
     return cudaGetLastError();
 }
 
 }  // namespace
+
+#ifdef NTM_TCS_TRACE
+extern "C" __attribute__((visibility("default"))) int ntm_debug_tcs_trace(long long* dst)
+{
+    return (int)cudaMemcpyFromSymbol(dst, g_tcs_trace, sizeof(long long) * 2 * 256 * 3);
+}
+#endif
 
 // host: the warp-uniform per-unit constants of the stream-major kernel, from the fp32 part of the blob
 void fill_tcs_consts(const float* blob_host, TcsConsts* kc)
@@ -272,14 +359,32 @@ void fill_tcs_consts(const float* blob_host, TcsConsts* kc)
     kc->bo = blob_host[BlobLayout::B_OUT];
 }
 
-// fmt: FMT_F16 / FMT_BF16.  tiles: 128-stream tiles per CTA (1 or 2; 0 = automatic).  Plain GRU only (a.d == nullptr).
-cudaError_t launch_gru_tcs(const GruArgs& a, const TcsConsts& kc, int fmt, int sm_count, int tiles, cudaStream_t st)
+template <int FMT, int TILES>
+cudaError_t launch_tcs_var(const GruArgs& a, const TcsConsts& kc, int var, cudaStream_t st)
+{
+    switch (var) {      // experiments: (var & 15) = VAR bits, (var & 16) = two threads per stream
+        case 0: return launch_tcs_one<FMT, TILES, 1, 0>(a, kc, st);
+        case 1: return launch_tcs_one<FMT, TILES, 1, 1>(a, kc, st);
+        case 2: return launch_tcs_one<FMT, TILES, 1, 2>(a, kc, st);
+        case 3: return launch_tcs_one<FMT, TILES, 1, 3>(a, kc, st);
+        case 16: return launch_tcs_one<FMT, TILES, 2, 0>(a, kc, st);
+        case 17: return launch_tcs_one<FMT, TILES, 2, 1>(a, kc, st);
+        case 18: return launch_tcs_one<FMT, TILES, 2, 2>(a, kc, st);
+        case 19: return launch_tcs_one<FMT, TILES, 2, 3>(a, kc, st);
+        case 23: return launch_tcs_one<FMT, TILES, 2, 7>(a, kc, st);
+        default: return launch_tcs_one<FMT, TILES, TCS_DEFAULT_UW, TCS_DEFAULT_VAR>(a, kc, st);
+    }
+}
+
+// fmt: FMT_F16 / FMT_BF16.  tiles: 128-stream tiles per CTA (1 or 2; 0 = automatic); var: kernel variant (experiments;
+// -1 = default).  Plain GRU only (a.d == nullptr).
+cudaError_t launch_gru_tcs(const GruArgs& a, const TcsConsts& kc, int fmt, int sm_count, int tiles, int var, cudaStream_t st)
 {
     if (a.B <= 0 || a.T <= 0) return cudaSuccess;
     if (a.d != nullptr) return cudaErrorInvalidValue;
     if (tiles <= 0) tiles = a.B > (long long)sm_count * TS_M ? 2 : 1;
-    if (fmt == FMT_BF16) return tiles >= 2 ? launch_tcs_one<FMT_BF16, 2>(a, kc, st) : launch_tcs_one<FMT_BF16, 1>(a, kc, st);
-    return tiles >= 2 ? launch_tcs_one<FMT_F16, 2>(a, kc, st) : launch_tcs_one<FMT_F16, 1>(a, kc, st);
+    if (fmt == FMT_BF16) return tiles >= 2 ? launch_tcs_var<FMT_BF16, 2>(a, kc, var, st) : launch_tcs_var<FMT_BF16, 1>(a, kc, var, st);
+    return tiles >= 2 ? launch_tcs_var<FMT_F16, 2>(a, kc, var, st) : launch_tcs_var<FMT_F16, 1>(a, kc, var, st);
 }
 
 }  // namespace ntm

@@ -59,6 +59,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 {
     while (!mbar_try_wait(bar, parity)) {}
 }
+// the same with a suspend-time hint (ns): the waiting thread sleeps in hardware instead of spinning through the
+// scheduler, which matters when the waiter shares an SM sub-partition with warps that do the math
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, uint32_t hint_ns = 20000u)
+{
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+            : "memory");
+    } while (!ok);
+}
 
 // ---- proxies / fences -----------------------------------------------------------------------------------
 // generic-proxy shared-memory writes -> visible to the async proxy (tcgen05.mma operand reads)
