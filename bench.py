@@ -375,15 +375,30 @@ def aux_measurements(ntm_b200, signals, dev, mode):
     per_mode["f16_tcgen05_kernel"] = timed(x2, mb, (32, 2))
     out["cfg2_samples_per_s_by_mode"] = per_mode
     del x2
-    # throughput regime (cfg 4 per-GPU widths): both tensor-core kernels
+    # throughput regime (cfg 4 per-GPU widths): the three tensor-core kernels.  "auto" is what the dispatcher picks
+    # (mma.sync below ~110 streams per SM, the stream-major tcgen05 kernel above); sm_count x 256 streams is the
+    # width at which every SM owns exactly two 128-stream tiles (no partial wave).
     big = {}
-    for Bb, Tb in ((8192, 12000), (65536, 3000)):
+    sms = L.ntm_query(lib.Q_SM_COUNT)
+    for Bb, Tb in ((8192, 12000), (sms * 256, 3000), (65536, 3000)):
         xb = signals.stream_batch_device(Bb, Tb, dev, dur=10.0).reshape(Bb, 1, Tb)
         mb.mode = "f16"
-        big[str(Bb)] = {"mma_sync": timed(xb, mb, (8, 3)), "tcgen05": timed(xb, mb, (32, 2))}
+        big[str(Bb)] = {"auto": timed(xb, mb), "auto_kernel": lib.KERNEL_NAMES.get(L.ntm_query(lib.Q_LAST_KERNEL), "?"),
+                        "mma_sync": timed(xb, mb, (8, 3)), "tcgen05_weight_stationary": timed(xb, mb, (32, 2))}
+        if Bb >= sms * 64:
+            big[str(Bb)]["tcgen05_stream_major"] = timed(xb, mb, (2 if Bb > sms * 128 else 1, 4))
         mb.mode = "fp32"
         big[str(Bb)]["fp32_cuda_core"] = timed(xb, mb)
         del xb
+    # roofline of the throughput regime at the balanced width: tensor FLOP/s against the measured dense peak, and the
+    # MUFU bound of the stream-major kernel (4 MUFU per unit-step: 3 ex2 + 2 shared reciprocals / 2)
+    bal = big[str(sms * 256)]["auto"]
+    tensor_peak = measured_peaks()[0]
+    out["large_batch_roofline"] = {
+        "streams": sms * 256, "samples_per_s": bal, "kernel": big[str(sms * 256)]["auto_kernel"],
+        "tensor_tflops": bal * FLOP_PER_SAMPLE / 1e12, "frac_of_measured_bf16_peak": bal * FLOP_PER_SAMPLE / 1e12 / tensor_peak,
+        "mufu_bound_samples_per_s_at_max_clock": sms * 16 * 1.965e9 / (64 * 4.0),
+        "frac_of_mufu_bound": bal / (sms * 16 * 1.965e9 / (64 * 4.0))}
     out["large_batch_samples_per_s"] = big
     # cfg 3: DiffDelGRU (GRU + fused fractional-delay read), 256 streams x 30 s, predict() semantics
     Bd, Td = 256, 30 * FS

@@ -24,6 +24,8 @@
 //   epilogue: tcgen05.st (new A) -> wait::st -> fence::before_thread_sync -> arrive(h_ready[tile])      (count 4)
 //   issuer:   wait(h_ready) -> fence::after_thread_sync -> 5 x tcgen05.mma -> tcgen05.commit(acc_full[tile])
 // x is prefetched two steps ahead by the owning thread, y is written by the owning thread (partial sectors merge in L2).
+#include <math.h>
+
 #include "gates.cuh"
 #include "tc_prims.cuh"
 
@@ -43,6 +45,7 @@ constexpr uint32_t TS_OFF_BAR = TS_B_BYTES;                       // 6 mbarriers
 constexpr uint32_t TS_OFF_YP = TS_OFF_BAR + 64;                   // [2 tiles][2][128] floats
 constexpr uint32_t TS_SMEM_BYTES = TS_OFF_YP + 2 * 2 * 128 * 4;
 constexpr int TS_UG = 8;                   // hidden units per TMEM load group
+bool g_tcs_dynamic = true;                  // experiments: (var & 32) switches the dynamic schedule off
 constexpr int TCS_DEFAULT_UW = 2;           // two threads per stream (measured best)
 constexpr int TCS_DEFAULT_VAR = 3;          // staggered tiles + reciprocal shared by two units
 
@@ -57,6 +60,13 @@ __device__ long long g_tcs_trace[2 * 256 * 3];
 #else
 #define TCS_STAMP(slot) do {} while (0)
 #endif
+
+// dynamic schedule of one launch (all null / 0: static)
+struct TcsSched {
+    unsigned long long* counter;   // next job
+    int* flags;                    // [group]: time chunks completed
+    int n_groups, n_chunks, chunk_T;
+};
 
 template <int FMT>
 __device__ __forceinline__ uint32_t pack_op(float lo, float hi)
@@ -85,7 +95,8 @@ __device__ __forceinline__ void tmem_st2(uint32_t taddr, uint32_t r0, uint32_t r
 // Gate math of one tile: one thread = one stream (UW == 1) or one NU-unit slice of it (UW == 2, slice UH).
 template <int FMT, int TILES, int UW, int VAR, int UH>
 __device__ __forceinline__ void tcs_epilogue(const GruArgs& a, const TcsConsts& kc, int tile, int wq, int lane, uint32_t tmem,
-                                             uint64_t* bars, float* ypart)
+                                             uint64_t* bars, float* ypart, long long group, long long t0, int nsteps,
+                                             long long base)
 {
     constexpr bool STAGGER = (VAR & 1) != 0 && TILES == 2, SHARE4 = (VAR & 2) != 0;
     constexpr int NPOLY = (VAR >> 2) & 3;
@@ -94,15 +105,16 @@ __device__ __forceinline__ void tcs_epilogue(const GruArgs& a, const TcsConsts& 
     constexpr bool PREFETCH = UW == 1;           // double-buffered accumulator loads (registers allow it only for UW == 1)
     constexpr int uh = UH, u0 = UH * NU;
     const int s = wq * 32 + lane;            // stream inside the tile == TMEM lane
-    const long long b0 = ((long long)blockIdx.x * TILES + tile) * TS_M;
+    const long long b0 = (group * TILES + tile) * TS_M;
     const int ns = (int)((a.B - b0) < (long long)TS_M ? (a.B - b0) : (long long)TS_M);   // may be <= 0
-    // both tiles of the CTA are live (the stagger protocol needs a partner)
-    const bool stagger = STAGGER && ((long long)blockIdx.x * TILES + 1) * TS_M < a.B;
+    // both tiles of the group are live (the stagger protocol needs a partner)
+    const bool stagger = STAGGER && (group * TILES + 1) * TS_M < a.B;
     if (ns > 0) {
         const bool valid = s < ns;
         const long long row = b0 + (valid ? s : 0);
-        const float* __restrict__ xp = a.x + row * a.ldx;
-        float* __restrict__ yp = a.y + row * a.ldy;
+        const float* __restrict__ xp = a.x + row * a.ldx + t0;      // this job's time window
+        float* __restrict__ yp = a.y + row * a.ldy + t0;
+        const long long Trem = a.T - t0;                             // samples of x readable from xp
         const uint32_t t_acc = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(tile * TS_TILE_COLS);
         const uint32_t t_op = t_acc + TS_A_OFF;
         float* const yslot = ypart + tile * 2 * TS_M + s;
@@ -110,7 +122,11 @@ __device__ __forceinline__ void tcs_epilogue(const GruArgs& a, const TcsConsts& 
         // ---- initial state: fp32 in registers, rounded copy + the first input sample into the A operand ----
         float h[NU];
 #pragma unroll
-        for (int j = 0; j < NU; ++j) h[j] = (valid && a.h_in) ? a.h_in[row * 64 + u0 + j] : 0.0f;
+        for (int j = 0; j < NU; ++j) {
+            // a later time chunk continues from the state its predecessor (possibly another SM) left in h_out: L2 reads
+            if (t0 > 0) h[j] = valid ? __ldcg(a.h_out + row * 64 + u0 + j) : 0.0f;
+            else h[j] = (valid && a.h_in) ? a.h_in[row * 64 + u0 + j] : 0.0f;
+        }
 #pragma unroll
         for (int g = 0; g < NG; ++g) {
             uint32_t w[4];
@@ -119,7 +135,7 @@ __device__ __forceinline__ void tcs_epilogue(const GruArgs& a, const TcsConsts& 
             tmem_st4(t_op + u0 / 2 + 4 * g, w);
         }
         float x0 = valid ? xp[0] : 0.0f;
-        float x1 = (valid && a.T > 1) ? xp[1] : 0.0f;
+        float x1 = (valid && Trem > 1) ? xp[1] : 0.0f;
         float xprev = 0.0f, yprev = 0.0f;    // UW == 2: this thread's head partial / input sample of the previous step
         if (uh == 0) {
             // K augmentation, columns 32..39 = k 64..79: [x_hi, x_lo | x_hi, 1 | 1, 0 | 0 ...]
@@ -134,16 +150,17 @@ __device__ __forceinline__ void tcs_epilogue(const GruArgs& a, const TcsConsts& 
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars[tile]);
 
-        for (long long t = 0; t < a.T; ++t) {
-            const float x2 = (valid && t + 2 < a.T) ? __ldg(xp + t + 2) : 0.0f;
-            if (stagger && (tile == 1 || t > 0)) mbar_wait_sleep(&bars[4 + (tile ^ 1)], (uint32_t)((t - (tile == 0)) & 1));
-            mbar_wait_sleep(&bars[2 + tile], (uint32_t)(t & 1));
+        for (int t = 0; t < nsteps; ++t) {
+            const float x2 = (valid && t + 2 < Trem) ? __ldg(xp + t + 2) : 0.0f;
+            const long long gt = base + t;       // steps this CTA has run so far: the mbarrier phase counter
+            if (stagger && (tile == 1 || gt > 0)) mbar_wait_sleep(&bars[4 + (tile ^ 1)], (uint32_t)((gt - (tile == 0)) & 1));
+            mbar_wait_sleep(&bars[2 + tile], (uint32_t)(gt & 1));
             tc_fence_after();
             TCS_STAMP(0);
             if (UW == 2 && uh == 0 && t > 0) {
                 // the partner's head partial of the previous step (published before its h_ready arrive, which
                 // happens-before the commit this thread just observed)
-                float v = yprev + yslot[((t - 1) & 1) * TS_M];
+                float v = yprev + yslot[((gt - 1) & 1) * TS_M];
                 if (a.skip) v += xprev;
                 if (valid) yp[t - 1] = v;
             }
@@ -204,12 +221,12 @@ __device__ __forceinline__ void tcs_epilogue(const GruArgs& a, const TcsConsts& 
                 tmem_st2(t_op + 32, pack_op<FMT>(xh, x1 - xh), pack_op<FMT>(xh, 1.0f));
             }
             float v = (ys[0] + ys[1]) + (ys[2] + ys[3]);
-            if (UW == 2 && uh == 1) yslot[(t & 1) * TS_M] = v;
-            // release the next MMA batch of this tile
+            if (UW == 2 && uh == 1) yslot[(gt & 1) * TS_M] = v;
+            // release the next MMA batch of this tile (the job's last step has no successor here)
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bars[tile]);
+            if (lane == 0 && t + 1 < nsteps) mbar_arrive(&bars[tile]);
             TCS_STAMP(2);
 
             if (UW == 1) {
@@ -225,9 +242,9 @@ __device__ __forceinline__ void tcs_epilogue(const GruArgs& a, const TcsConsts& 
         if (UW == 2) {
             asm volatile("bar.sync %0, %1;" ::"r"(1 + tile), "r"(64 * 4) : "memory");     // last partials visible
             if (uh == 0 && valid) {
-                float v = yprev + yslot[((a.T - 1) & 1) * TS_M];
+                float v = yprev + yslot[((base + nsteps - 1) & 1) * TS_M];
                 if (a.skip) v += xprev;
-                yp[a.T - 1] = v;
+                yp[nsteps - 1] = v;
             }
         }
 
@@ -243,12 +260,12 @@ __device__ __forceinline__ void tcs_epilogue(const GruArgs& a, const TcsConsts& 
 //            own -- keeps the two tiles of a CTA in anti-phase); bit 1: reciprocal shared by two
 //            units (4.0 MUFU per unit-step); bits 2-3: ex2 evaluations per unit pair moved to the FMA pipe.
 template <int FMT, int TILES, int UW, int VAR>
-__global__ void __launch_bounds__(32 * (4 * UW + 1) * TILES, 1) gru_tcs_kernel(const GruArgs a, const __grid_constant__ TcsConsts kc)
+__global__ void __launch_bounds__(32 * (4 * UW + 1) * TILES, 1) gru_tcs_kernel(const GruArgs a, const __grid_constant__ TcsConsts kc, const TcsSched sc)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* const bop = smem;
     uint64_t* const bars = reinterpret_cast<uint64_t*>(smem + TS_OFF_BAR);    // [tile]: h_ready, [2 + tile]: acc_full, [4 + tile]: mid
-    uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(smem + TS_OFF_BAR + 56);
+    uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(smem + TS_OFF_BAR + 48);
     float* const ypart = reinterpret_cast<float*>(smem + TS_OFF_YP);          // [tile][2][128] head partials (UW == 2)
 
     const int tid = threadIdx.x;
@@ -286,30 +303,77 @@ __global__ void __launch_bounds__(32 * (4 * UW + 1) * TILES, 1) gru_tcs_kernel(c
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    if (warp >= EPI_WARPS) {
-        // ================================ MMA issue warp of one tile ==========================================
-        const int tile = warp - EPI_WARPS;
-        const long long b0 = ((long long)blockIdx.x * TILES + tile) * TS_M;
-        if (b0 < a.B && elect_one()) {
-            constexpr uint32_t idesc = instr_desc(FMT, TS_M, TS_N);
-            const uint32_t d_base = tmem + (uint32_t)(tile * TS_TILE_COLS);
-            const uint32_t a_base = d_base + TS_A_OFF;
-            const uint32_t b_base = smem_u32(bop);
-            for (long long t = 0; t < a.T; ++t) {
-                mbar_wait_sleep(&bars[tile], (uint32_t)(t & 1));
-                tc_fence_after();
-#pragma unroll
-                for (int ks = 0; ks < TS_NK; ++ks)
-                    mma_ts<FMT>(d_base, a_base + ks * 8, smem_desc(b_base + ks * 2 * TS_LBO, TS_LBO, TS_SBO), idesc, ks > 0);
-                mma_commit(&bars[2 + tile]);
+    // ---- job loop.  A job = one group of TILES consecutive 128-stream tiles x one time chunk.  Static schedule
+    // (sc.counter == nullptr): the CTA runs group blockIdx.x over all T steps.  Dynamic schedule (more groups than SMs):
+    // a persistent grid pulls (group, chunk) jobs from a global counter, chunk-major, so that whole SMs never idle in a
+    // partial last wave; a group's state travels between chunks (and SMs) through h_out, guarded by a per-group
+    // progress flag (release/acquire at GPU scope).
+    int* const job_slot = reinterpret_cast<int*>(smem + TS_OFF_BAR + 52);
+    long long base = 0;                          // steps this CTA has run so far
+    for (long long it = 0;; ++it) {
+        long long group, t0;
+        int nsteps;
+        if (sc.counter == nullptr) {
+            if (it > 0) break;
+            group = blockIdx.x; t0 = 0; nsteps = (int)a.T;
+        } else {
+            if (tid == 0) {
+                const unsigned long long job = atomicAdd(sc.counter, 1ull);
+                int chunk = -1;
+                if (job < (unsigned long long)sc.n_groups * sc.n_chunks) {
+                    chunk = (int)(job / sc.n_groups);
+                    const long long grp = (long long)(job % sc.n_groups);
+                    while (*reinterpret_cast<volatile int*>(sc.flags + grp) < chunk) __nanosleep(200);
+                    __threadfence();
+                    job_slot[1] = (int)grp;
+                }
+                job_slot[0] = chunk;
             }
+            __syncthreads();
+            const int chunk = job_slot[0];
+            if (chunk < 0) break;
+            group = job_slot[1];
+            t0 = (long long)chunk * sc.chunk_T;
+            nsteps = (int)((a.T - t0) < (long long)sc.chunk_T ? (a.T - t0) : (long long)sc.chunk_T);
         }
-    } else {
-        // ================================ epilogue warps ===========================================================
-        const int tile = warp / (4 * UW);
-        const int wq = warp & 3;                 // TMEM lane quarter (== warp id % 4)
-        if (UW == 1 || ((warp >> 2) & 1) == 0) tcs_epilogue<FMT, TILES, UW, VAR, 0>(a, kc, tile, wq, lane, tmem, bars, ypart);
-        else tcs_epilogue<FMT, TILES, UW, VAR, UW - 1>(a, kc, tile, wq, lane, tmem, bars, ypart);
+
+        if (warp >= EPI_WARPS) {
+            // ================================ MMA issue warp of one tile ======================================
+            const int tile = warp - EPI_WARPS;
+            const long long b0 = (group * TILES + tile) * TS_M;
+            if (b0 < a.B && elect_one()) {
+                constexpr uint32_t idesc = instr_desc(FMT, TS_M, TS_N);
+                const uint32_t d_base = tmem + (uint32_t)(tile * TS_TILE_COLS);
+                const uint32_t a_base = d_base + TS_A_OFF;
+                const uint32_t b_base = smem_u32(bop);
+                for (int t = 0; t < nsteps; ++t) {
+                    mbar_wait_sleep(&bars[tile], (uint32_t)((base + t) & 1));
+                    tc_fence_after();
+#pragma unroll
+                    for (int ks = 0; ks < TS_NK; ++ks)
+                        mma_ts<FMT>(d_base, a_base + ks * 8, smem_desc(b_base + ks * 2 * TS_LBO, TS_LBO, TS_SBO), idesc, ks > 0);
+                    mma_commit(&bars[2 + tile]);
+                }
+            }
+        } else {
+            // ================================ epilogue warps ======================================================
+            const int tile = warp / (4 * UW);
+            const int wq = warp & 3;                 // TMEM lane quarter (== warp id % 4)
+            if (UW == 1 || ((warp >> 2) & 1) == 0)
+                tcs_epilogue<FMT, TILES, UW, VAR, 0>(a, kc, tile, wq, lane, tmem, bars, ypart, group, t0, nsteps, base);
+            else
+                tcs_epilogue<FMT, TILES, UW, VAR, UW - 1>(a, kc, tile, wq, lane, tmem, bars, ypart, group, t0, nsteps, base);
+        }
+        base += nsteps;
+
+        // end of the job: every role is done with TMEM and the barriers' phases agree again
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        if (sc.counter != nullptr && tid == 0) {
+            __threadfence();                                       // the group's h_out is visible GPU-wide ...
+            atomicExch(sc.flags + group, (int)(t0 / sc.chunk_T) + 1);   // ... before its next chunk may start
+        }
     }
 
     // ---- teardown: every MMA has completed (the epilogue consumed the last accumulator) ------------------------
@@ -319,7 +383,7 @@ __global__ void __launch_bounds__(32 * (4 * UW + 1) * TILES, 1) gru_tcs_kernel(c
 }
 
 template <int FMT, int TILES, int UW, int VAR>
-cudaError_t launch_tcs_one(const GruArgs& a, const TcsConsts& kc, cudaStream_t st)
+cudaError_t launch_tcs_one(const GruArgs& a, const TcsConsts& kc, int sm_count, cudaStream_t st)
 {
     static bool configured[64] = {};
     int dev = 0;
@@ -331,11 +395,39 @@ cudaError_t launch_tcs_one(const GruArgs& a, const TcsConsts& kc, cudaStream_t s
         if (e != cudaSuccess) return e;
         configured[dev] = true;
     }
-    const long long per_cta = (long long)TS_M * TILES;
-    const long long grid = (a.B + per_cta - 1) / per_cta;
-    gru_tcs_kernel<FMT, TILES, UW, VAR><<<(unsigned)grid, 32 * (4 * UW + 1) * TILES, TS_SMEM_BYTES, st>>>(a, kc);
+    const long long per_group = (long long)TS_M * TILES;
+    const long long groups = (a.B + per_group - 1) / per_group;
+    TcsSched sc{};
+    long long grid = groups;
+    // More groups than SMs and a partial last wave: pull (group, time chunk) jobs dynamically.  Chunk length: a job
+    // costs ~7 steps of overhead (state round trip through L2, pipeline fill/drain; measured) and the tail idles half a
+    // job per SM on average, so ct ~ sqrt(2 * 7 * T * groups / SMs), as a power of two in 64 .. 1024.
+    if (groups > sm_count && groups % sm_count != 0 && groups < (1ll << 30) && g_tcs_dynamic) {
+        const double ct = sqrt(14.0 * (double)a.T * (double)groups / (double)sm_count);
+        long long p2 = 64;
+        while (p2 * 1.41 <= ct && p2 < 1024) p2 *= 2;
+        const long long chunks = (a.T + p2 - 1) / p2;
+        if (chunks > 1 && chunks < (1ll << 30)) {
+            void* scratch = nullptr;
+            const size_t bytes = 16 + sizeof(int) * (size_t)groups;
+            e = cudaMallocAsync(&scratch, bytes, st);               // stream-ordered: no device synchronisation
+            if (e != cudaSuccess) return e;
+            e = cudaMemsetAsync(scratch, 0, bytes, st);
+            if (e != cudaSuccess) return e;
+            sc.counter = static_cast<unsigned long long*>(scratch);
+            sc.flags = reinterpret_cast<int*>(static_cast<char*>(scratch) + 16);
+            sc.n_groups = (int)groups; sc.n_chunks = (int)chunks; sc.chunk_T = (int)p2;
+            grid = sm_count;
+        }
+    }
+    gru_tcs_kernel<FMT, TILES, UW, VAR><<<(unsigned)grid, 32 * (4 * UW + 1) * TILES, TS_SMEM_BYTES, st>>>(a, kc, sc);
     ++g_launches;
-    return cudaGetLastError();
+    e = cudaGetLastError();
+    if (sc.counter) {
+        const cudaError_t e2 = cudaFreeAsync(sc.counter, st);
+        if (e == cudaSuccess) e = e2;
+    }
+    return e;
 }
 
 }  // namespace
@@ -359,22 +451,29 @@ void fill_tcs_consts(const float* blob_host, TcsConsts* kc)
     kc->bo = blob_host[BlobLayout::B_OUT];
 }
 
+namespace {
+
 template <int FMT, int TILES>
-cudaError_t launch_tcs_var(const GruArgs& a, const TcsConsts& kc, int var, cudaStream_t st)
+cudaError_t launch_tcs_var(const GruArgs& a, const TcsConsts& kc, int var, int sm_count, cudaStream_t st)
 {
-    switch (var) {      // experiments: (var & 15) = VAR bits, (var & 16) = two threads per stream
-        case 0: return launch_tcs_one<FMT, TILES, 1, 0>(a, kc, st);
-        case 1: return launch_tcs_one<FMT, TILES, 1, 1>(a, kc, st);
-        case 2: return launch_tcs_one<FMT, TILES, 1, 2>(a, kc, st);
-        case 3: return launch_tcs_one<FMT, TILES, 1, 3>(a, kc, st);
-        case 16: return launch_tcs_one<FMT, TILES, 2, 0>(a, kc, st);
-        case 17: return launch_tcs_one<FMT, TILES, 2, 1>(a, kc, st);
-        case 18: return launch_tcs_one<FMT, TILES, 2, 2>(a, kc, st);
-        case 19: return launch_tcs_one<FMT, TILES, 2, 3>(a, kc, st);
-        case 23: return launch_tcs_one<FMT, TILES, 2, 7>(a, kc, st);
-        default: return launch_tcs_one<FMT, TILES, TCS_DEFAULT_UW, TCS_DEFAULT_VAR>(a, kc, st);
+    g_tcs_dynamic = var < 0 || (var & 32) == 0;
+    if (var >= 0) var &= 31;
+    switch (var) {      // experiments: (var & 15) = VAR bits, (var & 16) = two threads per stream, (var & 32) = static
+        case 0: return launch_tcs_one<FMT, TILES, 1, 0>(a, kc, sm_count, st);
+        case 1: return launch_tcs_one<FMT, TILES, 1, 1>(a, kc, sm_count, st);
+        case 2: return launch_tcs_one<FMT, TILES, 1, 2>(a, kc, sm_count, st);
+        case 3: return launch_tcs_one<FMT, TILES, 1, 3>(a, kc, sm_count, st);
+        case 16: return launch_tcs_one<FMT, TILES, 2, 0>(a, kc, sm_count, st);
+        case 17: return launch_tcs_one<FMT, TILES, 2, 1>(a, kc, sm_count, st);
+        case 18: return launch_tcs_one<FMT, TILES, 2, 2>(a, kc, sm_count, st);
+        case 19: return launch_tcs_one<FMT, TILES, 2, 3>(a, kc, sm_count, st);
+        case 23: return launch_tcs_one<FMT, TILES, 2, 7>(a, kc, sm_count, st);
+        case 31: return launch_tcs_one<FMT, TILES, TCS_DEFAULT_UW, TCS_DEFAULT_VAR>(a, kc, sm_count, st);
+        default: return launch_tcs_one<FMT, TILES, TCS_DEFAULT_UW, TCS_DEFAULT_VAR>(a, kc, sm_count, st);
     }
 }
+
+}  // namespace
 
 // fmt: FMT_F16 / FMT_BF16.  tiles: 128-stream tiles per CTA (1 or 2; 0 = automatic); var: kernel variant (experiments;
 // -1 = default).  Plain GRU only (a.d == nullptr).
@@ -382,9 +481,10 @@ cudaError_t launch_gru_tcs(const GruArgs& a, const TcsConsts& kc, int fmt, int s
 {
     if (a.B <= 0 || a.T <= 0) return cudaSuccess;
     if (a.d != nullptr) return cudaErrorInvalidValue;
-    if (tiles <= 0) tiles = a.B > (long long)sm_count * TS_M ? 2 : 1;
-    if (fmt == FMT_BF16) return tiles >= 2 ? launch_tcs_var<FMT_BF16, 2>(a, kc, var, st) : launch_tcs_var<FMT_BF16, 1>(a, kc, var, st);
-    return tiles >= 2 ? launch_tcs_var<FMT_F16, 2>(a, kc, var, st) : launch_tcs_var<FMT_F16, 1>(a, kc, var, st);
+    // one tile per SM (time-multiplexed by the job queue) beats two resident tiles until ~190 streams per SM (measured)
+    if (tiles <= 0) tiles = a.B >= 190ll * sm_count ? 2 : 1;
+    if (fmt == FMT_BF16) return tiles >= 2 ? launch_tcs_var<FMT_BF16, 2>(a, kc, var, sm_count, st) : launch_tcs_var<FMT_BF16, 1>(a, kc, var, sm_count, st);
+    return tiles >= 2 ? launch_tcs_var<FMT_F16, 2>(a, kc, var, sm_count, st) : launch_tcs_var<FMT_F16, 1>(a, kc, var, sm_count, st);
 }
 
 }  // namespace ntm

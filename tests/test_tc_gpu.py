@@ -225,3 +225,26 @@ def test_stream_major_kernel_large_batch():
         yb, _ = run(x)
         assert lib.query(lib.Q_LAST_KERNEL) == 3 and bool(torch.isfinite(yb).all())
         assert float(((yb - y) ** 2).sum() / (y ** 2).sum()) <= 5e-2
+
+
+def test_stream_major_dynamic_schedule_is_exact():
+    """More tile groups than SMs with a partial last wave: the kernel pulls (group, time chunk) jobs from a queue and a
+    group's state migrates between SMs through h_out.  Results and final state must equal the static schedule's bit
+    for bit (tuning variant bit 32 forces the static schedule), for one and two tiles per CTA."""
+    m = make_rnn("cfg2", "f16")
+    sms = lib.query(lib.Q_SM_COUNT)
+    with torch.inference_mode():
+        m.initialize_hidden()
+        m.warm_start()
+        hw = m.hidden.clone()
+        for tiles, B, T in ((2, sms * 256 + 300, 700), (1, sms * 128 + 1000, 900)):
+            x = signals.stream_batch_device(B, T, DEV, dur=10.0).reshape(B, 1, T)
+            outs = []
+            for var in (31, 63):                                  # default variant: dynamic, static
+                lib.load().ntm_set_tuning(tiles + 4 * (var + 1), 4)
+                m.hidden = hw.expand(1, B, 64).contiguous()
+                outs.append((m(x), m.hidden.clone()))
+                assert lib.query(lib.Q_LAST_KERNEL) == 3
+            assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+            assert bool(torch.isfinite(outs[0][0]).all())
+            del x, outs
