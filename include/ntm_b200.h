@@ -119,8 +119,10 @@ int ntm_diffdel_predict_host(void* handle, int mode, const float* x_host, const 
                              float* y_host, float* pre_d_host, float* h_host, float* hist_host,
                              int64_t B, int64_t T, int64_t D, int skip, int64_t chunk_T);
 
-/* Tuning knob for experiments (0 = automatic).  fp32 kernel: streams per CTA / k-split.  Tensor-core kernel:
- * streams per group (8, 16, 32, 64) / groups per CTA (1, 2). */
+/* Tuning knob for experiments and tests (0, 0 = automatic dispatch).  fp32 kernel: streams per CTA / k-split.
+ * Tensor-core modes, by the second argument: 1|2 weight-stationary tcgen05 kernel (first = streams per group 32|64),
+ * 3 warp-level mma.sync kernel (first = streams per CTA 8|16), 4 stream-major tcgen05 kernel (first = 128-stream
+ * tiles per CTA 1|2, + 4 * (variant + 1) for kernel variants).  Process-global, not thread-safe. */
 int ntm_set_tuning(int streams_per_cta, int ksplit);
 
 #if defined(__GNUC__)
