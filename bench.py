@@ -416,6 +416,23 @@ def aux_measurements(ntm_b200, signals, dev, mode):
         cfg3[mdm] = Bd * Td / (e0.elapsed_time(e1) * 1e-3)
         del yd, pd
     out["cfg3_diffdel_256x30s_samples_per_s"] = cfg3
+    del xd, dd
+    # evaluation losses on the device: one pass over 1024 streams x 30 s of (output, target);
+    # HBM-bound by construction: 8 algorithmic bytes per sample against the measured copy bandwidth
+    Bl, Tl = 1024, 30 * FS
+    tl = 0.2 * torch.randn(Bl, 1, Tl, device=dev)
+    ol = tl + 0.02 * torch.randn(Bl, 1, Tl, device=dev)
+    hbm_peak = measured_peaks()[1]
+    losses = {}
+    for name, fn in (("ESR", ntm_b200.ESRLoss()), ("DCPreESR", ntm_b200.DCPreESR())):
+        fn(ol, tl)
+        best = 1e9
+        for _ in range(3):
+            e0.record(); fn(ol, tl); e1.record(); torch.cuda.synchronize(dev)
+            best = min(best, e0.elapsed_time(e1))
+        gbs = 8.0 * Bl * Tl / (best * 1e-3) / 1e9
+        losses[name] = {"samples_per_s": Bl * Tl / (best * 1e-3), "hbm_gbs": gbs, "frac_of_measured_hbm_peak": gbs / hbm_peak}
+    out["loss_pass_1024x30s"] = losses
     return out
 
 

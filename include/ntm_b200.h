@@ -105,6 +105,18 @@ int ntm_delay_forward(const float* x, int64_t ldx, const float* d, int64_t ldd, 
 int ntm_delay_check(const float* d, int64_t ldd, int64_t B, int64_t T, int64_t D, int device, void* stream);
 
 /*
+ * Evaluation losses on the device (the step right after the recurrent path, code/test-model.py:250-253,386-388).
+ * Replaces: ESRLoss, code/Automated_GuitarAmpModelling/CoreAudioML/training.py:5-16 (dc_pre == 0) and
+ * ESRLoss(dc_pre=True) = DC_PreEmph + ESR, code/GreyBoxDRC/loss_funcs.py:6-52 (dc_pre != 0: 2000-tap truncation of
+ * (1 - z^-1)/(1 - 0.995 z^-1) applied to both signals, zero-padded in front).
+ *   out, target: B rows of T samples (row strides ldo, ldt), the reference's (B,1,T) tensors.
+ *   sums (DEVICE, 2 doubles, written asynchronously): sum (f(t)-f(o))^2 and sum f(t)^2 over all B*T samples;
+ *   loss = (sums[0]/(B*T)) / (sums[1]/(B*T) + 1e-5).
+ */
+int ntm_esr_sums(const float* out, int64_t ldo, const float* target, int64_t ldt, int64_t B, int64_t T,
+                 int dc_pre, double* sums, int device, void* stream);
+
+/*
  * Whole-signal prediction from HOST buffers (page-locked for full speed): time-chunked H2D copy, kernel and
  * D2H copy pipelined on the engine's own streams.  Replaces the loop of RNN.predict, code/model.py:218-246
  * (host->device at code/test-model.py:427-433, device->host at :525).  SYNCHRONOUS.

@@ -414,6 +414,19 @@ int ntm_delay_check(const float* d, int64_t ldd, int64_t B, int64_t T, int64_t D
     return host_flag ? NTM_EDELAY : NTM_OK;
 }
 
+int ntm_esr_sums(const float* out, int64_t ldo, const float* target, int64_t ldt, int64_t B, int64_t T, int dc_pre,
+                 double* sums, int device, void* stream)
+{
+    if (B < 0 || T < 0 || !sums) return NTM_EINVAL;
+    if (B > 0 && T > 0 && (!out || !target || ldo < T || ldt < T)) return NTM_EINVAL;
+    DeviceGuard g(device);
+    if (!g.ok) return cuda_fail(cudaErrorInvalidDevice);
+    int sms = 0;
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    CU(ntm::launch_esr(out, ldo, target, ldt, B, T, dc_pre, sums, sms, (cudaStream_t)stream));
+    return NTM_OK;
+}
+
 int ntm_gru_predict_host(void* handle, int mode, const float* x_host, float* y_host, float* h_host, int64_t B,
                          int64_t T, int skip, int64_t chunk_T)
 {

@@ -65,6 +65,9 @@ cudaError_t launch_delay(const float* x, long long ldx, const float* d, long lon
 cudaError_t launch_delay_check(const float* d, long long ldd, long long B, long long T, long long D, int* flag_dev,
                                cudaStream_t st);
 
+cudaError_t launch_esr(const float* out, long long ldo, const float* tgt, long long ldt, long long B, long long T,
+                       int dc_pre, double* sums, int sm_count, cudaStream_t st);
+
 extern unsigned long long g_launches;   // engine kernels launched by this process (ntm_query)
 
 // ------------------------------------------------------------------------------------------------

@@ -40,6 +40,8 @@ def lib():
         _lib.ntm_oracle_delay_window_f32.argtypes = dl
         _lib.ntm_oracle_esr.argtypes = [_f32p, _f32p, _i64]
         _lib.ntm_oracle_esr.restype = ctypes.c_double
+        _lib.ntm_oracle_dcpre_esr.argtypes = [_f32p, _f32p, _i64, _i64, _i64, _i64, _f32p, _i64, _f64p]
+        _lib.ntm_oracle_dcpre_esr.restype = ctypes.c_double
     return _lib
 
 
@@ -148,3 +150,25 @@ def diffdel_predict(w, x, d, max_delay, skip=False):
     pre_d, h = gru_forward(w, x, h, skip)
     y, hist = delay_forward(pre_d, d, hist)
     return y, pre_d, h, hist
+
+
+def dcpre_taps(R=0.995, n=2000):
+    """The reference's pre-emphasis impulse response (code/GreyBoxDRC/loss_funcs.py:10-11), float32:
+    scipy.signal.dimpulse of (1 - z^-1)/(1 - R z^-1), n samples."""
+    import scipy.signal as signal
+    _, ir = signal.dimpulse(signal.dlti([1, -1], [1, -R]), n=n)
+    return np.ascontiguousarray(ir[0][:, 0].astype(np.float32))
+
+
+def dcpre_esr(out, target, dc_pre=True):
+    """ESRLoss(dc_pre) of code/GreyBoxDRC/loss_funcs.py:32-52 (dc_pre=False: CoreAudioML/training.py:10-16) on
+    (B, T) or (B, 1, T) arrays; returns (loss, sum_num, sum_den)."""
+    o = _c32(out)
+    t = _c32(target)
+    o = o.reshape(-1, o.shape[-1])
+    t = t.reshape(-1, t.shape[-1])
+    taps = dcpre_taps() if dc_pre else None
+    sums = np.zeros(2, dtype=np.float64)
+    loss = lib().ntm_oracle_dcpre_esr(_p32(o), _p32(t), o.shape[0], o.shape[1], o.shape[1], t.shape[1],
+                                      _p32(taps), 0 if taps is None else taps.shape[0], sums.ctypes.data_as(_f64p))
+    return float(loss), float(sums[0]), float(sums[1])

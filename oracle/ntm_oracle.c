@@ -228,3 +228,46 @@ double ntm_oracle_esr(const float* out, const float* target, int64_t n)
     if (n > 0) { num /= (double)n; den /= (double)n; }
     return num / (den + 1e-5);
 }
+
+/*
+ * DC pre-emphasised error-to-signal ratio ("DCPreESR"), code/GreyBoxDRC/loss_funcs.py:6-52 as called by
+ * code/test-model.py:250-253,386-388 on (B,1,T) tensors.
+ *   DC_PreEmph (:6-30): both signals are zero-padded by 1999 samples at the front and correlated with the flipped
+ *   2000-sample impulse response of H(z) = (1 - z^-1) / (1 - R z^-1), R = 0.995 (scipy.signal.dimpulse, cast to
+ *   float32), i.e. a causal 2000-tap FIR:  f[n] = sum_{k=0..1999} h[k] x[n-k],  h[0] = 1, h[k] = (R-1) R^(k-1).
+ *   ESRLoss (:32-52): mean((f_t - f_o)^2) / (mean(f_t^2) + 1e-5), means over ALL B*T elements.
+ * `taps` holds h[0..ntaps-1] in float32 exactly as the reference builds them (tests pass the scipy values);
+ * products and sums are carried in double (the reference's fp32 conv1d differs from this by its own round-off).
+ * ntaps == 0: no filter (CoreAudioML/training.py:10-16).  Returns the loss; sums[0..1] (optional) get the two sums.
+ */
+NTM_ORACLE_EXPORT
+double ntm_oracle_dcpre_esr(const float* out, const float* target, int64_t B, int64_t T, int64_t ldo, int64_t ldt,
+                            const float* taps, int64_t ntaps, double* sums)
+{
+    double num = 0.0, den = 0.0;
+    for (int64_t b = 0; b < B; ++b) {
+        const float* o = out + b * ldo;
+        const float* t = target + b * ldt;
+        for (int64_t n = 0; n < T; ++n) {
+            double ft, fe;
+            if (ntaps == 0) {
+                ft = (double)t[n];
+                fe = (double)t[n] - (double)o[n];
+            } else {
+                ft = 0.0;
+                double fo = 0.0;
+                const int64_t kmax = n < ntaps - 1 ? n : ntaps - 1;
+                for (int64_t k = kmax; k >= 0; --k) {
+                    ft += (double)taps[k] * (double)t[n - k];
+                    fo += (double)taps[k] * (double)o[n - k];
+                }
+                fe = ft - fo;
+            }
+            num += fe * fe;
+            den += ft * ft;
+        }
+    }
+    if (sums) { sums[0] = num; sums[1] = den; }
+    const double cnt = (double)(B * T);
+    return cnt > 0 ? (num / cnt) / (den / cnt + 1e-5) : 0.0;
+}

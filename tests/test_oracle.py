@@ -109,3 +109,19 @@ def test_known_answers_baseline_md():
                       ("cfg3", -0.782204804, 2.725984538)):
         h = load_golden(f"golden_{tag}")["h_warm"].astype(np.float64)
         assert abs(h.sum() - s) < 1e-5 and abs(np.linalg.norm(h) - n) < 1e-5
+
+
+def test_dcpre_esr_oracle_vs_reference_golden():
+    """The C restatement of ESR / DCPreESR (ntm_oracle_dcpre_esr) against values the reference's own loss classes
+    produced (oracle/make_golden_loss.py: GreyBoxDRC.loss_funcs.ESRLoss(dc_pre=True), CoreAudioML ESRLoss)."""
+    import numpy as np
+    g = load_golden("golden_loss")
+    assert np.array_equal(c_oracle.dcpre_taps(), g["taps"])
+    assert g["taps"][0] == 1.0 and abs(g["taps"][1] + 0.005) < 1e-9 and len(g["taps"]) == 2000
+    for case in ("sweep_vs_perturbed", "dc_offset", "batch5", "short", "silence_target"):
+        dc, num, den = c_oracle.dcpre_esr(g[f"o_{case}"], g[f"t_{case}"], True)
+        pl, _, _ = c_oracle.dcpre_esr(g[f"o_{case}"], g[f"t_{case}"], False)
+        assert abs(dc - float(g[f"dcpre_{case}"])) <= 2e-5 * abs(float(g[f"dcpre_{case}"])) + 1e-9, case
+        assert abs(pl - float(g[f"esr_{case}"])) <= 2e-5 * abs(float(g[f"esr_{case}"])) + 1e-9, case
+        n = g[f"o_{case}"].size
+        assert abs(dc - (num / n) / (den / n + 1e-5)) < 1e-12
