@@ -87,9 +87,16 @@ struct MmaCfg {
     static constexpr int SMEM_BYTES = OFF_YP + 4 * CH * YP_LD * 4;
 };
 
-template <int FMT, int NT>
+// HALF (NT == 1 only): the CTA owns 4 streams, placed in the EVEN columns of its n8 tile (stream s <-> column 2s), and
+// skips the gate math, state stores and outputs of the odd columns: half the MUFU / FMA work per step for the same
+// MMAs -- the shorter dependent step wins whenever there are CTAs to spare (B <= 4 streams per SM: cfg 3, cfg 5).
+template <int FMT, int NT, bool HALF>
 __global__ void __launch_bounds__(128, FMT == FMT_TF32 ? 2 : 4) gru_mma_kernel(const GruArgs a)
 {
+    static_assert(!HALF || NT == 1, "HALF needs a single n8 tile");
+    constexpr int SC = HALF ? 4 : 8 * NT;            // streams per CTA
+    constexpr int CS = HALF ? 2 : 1;                 // column stride of a stream
+    constexpr int NE = HALF ? 1 : 2;                 // live columns per thread and n8 tile
     using C = MmaCfg<FMT, NT>;
     using F = Frag<FMT>;
     constexpr int S = C::S, CH = C::CH, NK = F::NK, BW = F::BW;
@@ -101,8 +108,8 @@ __global__ void __launch_bounds__(128, FMT == FMT_TF32 ? 2 : 4) gru_mma_kernel(c
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int gid = lane >> 2, tig = lane & 3;
     const int u0 = 16 * warp + 2 * gid, u1 = u0 + 1;      // adjacent units: their rounded states share a store
-    const long long b0 = (long long)blockIdx.x * S;
-    const int ns = (int)((a.B - b0) < (long long)S ? (a.B - b0) : (long long)S);
+    const long long b0 = (long long)blockIdx.x * SC;
+    const int ns = (int)((a.B - b0) < (long long)SC ? (a.B - b0) : (long long)SC);
     const float* __restrict__ blob = a.blob;
 
     // ---- W_hh fragments -> registers -------------------------------------------------------------------------
@@ -206,9 +213,9 @@ __global__ void __launch_bounds__(128, FMT == FMT_TF32 ? 2 : 4) gru_mma_kernel(c
         const int n = (int)((a.T - t0) < (long long)CH ? (a.T - t0) : (long long)CH);
         float* dstb = xs + buf * CH * S;
         for (int idx = tid; idx < CH * S; idx += 128) {
-            const int s = idx % S, tt = idx / S;
-            if (s < ns && tt < n) cp_async4(dstb + tt * S + s, a.x + (b0 + s) * a.ldx + t0 + tt);
-            else dstb[tt * S + s] = 0.0f;
+            const int col = idx % S, tt = idx / S, s = col / CS;
+            if (col % CS == 0 && s < ns && tt < n) cp_async4(dstb + tt * S + col, a.x + (b0 + s) * a.ldx + t0 + tt);
+            else dstb[tt * S + col] = 0.0f;
         }
         cp_async_commit();
     };
@@ -219,10 +226,12 @@ __global__ void __launch_bounds__(128, FMT == FMT_TF32 ? 2 : 4) gru_mma_kernel(c
     for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-            const int s = nt * 8 + 2 * tig + e;
+            const int col = nt * 8 + 2 * tig + e, s = col / CS;
+            const bool live = col % CS == 0 && s < ns;
 #pragma unroll
-            for (int u = 0; u < 2; ++u) hst[nt][u][e] = (s < ns && a.h_in) ? a.h_in[(b0 + s) * 64 + u0 + u] : 0.0f;
-            store_state2<FMT>(hb + s * F::ROW_BYTES, u0, hst[nt][0][e], hst[nt][1][e]);
+            for (int u = 0; u < 2; ++u) hst[nt][u][e] = (live && a.h_in) ? a.h_in[(b0 + s) * 64 + u0 + u] : 0.0f;
+            store_state2<FMT>(hb + col * F::ROW_BYTES, u0, hst[nt][0][e], hst[nt][1][e]);
+            store_state2<FMT>(hb + C::HB_BYTES + col * F::ROW_BYTES, u0, 0.0f, 0.0f);     // dead columns stay finite
         }
     load_x(0, 0);
 
@@ -273,14 +282,14 @@ __global__ void __launch_bounds__(128, FMT == FMT_TF32 ? 2 : 4) gru_mma_kernel(c
 #pragma unroll
                 for (int u = 0; u < 2; ++u)
 #pragma unroll
-                    for (int e = 0; e < 2; ++e)
+                    for (int e = 0; e < NE; ++e)
                         gates_rz_dn(uc[u], acc[nt][u][e], acc[nt][u][2 + e], acc[nt][2][2 * u + e], e ? xv.y : xv.x,
                                     z[u][e], dn[u][e]);
 #pragma unroll
-                for (int e = 0; e < 2; ++e)        // the two hidden units of one stream share the n-gate reciprocal
+                for (int e = 0; e < NE; ++e)       // the two hidden units of one stream share the n-gate reciprocal
                     gates_blend2(z[0][e], dn[0][e], hst[nt][0][e], z[1][e], dn[1][e], hst[nt][1][e], hn[0][e], hn[1][e]);
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
+                for (int e = 0; e < NE; ++e) {
                     hst[nt][0][e] = hn[0][e];
                     hst[nt][1][e] = hn[1][e];
                     store_state2<FMT>(hnext + (nt * 8 + 2 * tig + e) * F::ROW_BYTES, u0, hn[0][e], hn[1][e]);
@@ -304,19 +313,19 @@ __global__ void __launch_bounds__(128, FMT == FMT_TF32 ? 2 : 4) gru_mma_kernel(c
             __syncthreads();
         }
         // ---- flush the chunk: y = sum of the four warps' partials + bias (+ x) ------------------------------------
-        for (int idx = tid; idx < S * CH; idx += 128) {
-            const int s = idx / CH, tt = idx % CH;
+        for (int idx = tid; idx < SC * CH; idx += 128) {
+            const int s = idx / CH, tt = idx % CH, col = s * CS;
             if (s < ns && tt < n) {
-                float v = yp[tt * C::YP_LD + s] + yp[(CH + tt) * C::YP_LD + s] + yp[(2 * CH + tt) * C::YP_LD + s] +
-                          yp[(3 * CH + tt) * C::YP_LD + s] + bo;
-                if (a.skip) v += xcur[tt * S + s];
+                float v = yp[tt * C::YP_LD + col] + yp[(CH + tt) * C::YP_LD + col] + yp[(2 * CH + tt) * C::YP_LD + col] +
+                          yp[(3 * CH + tt) * C::YP_LD + col] + bo;
+                if (a.skip) v += xcur[tt * S + col];
                 head_out[(b0 + s) * ldo + t0 + tt] = v;
                 if (delay && a.warmup) a.y[(b0 + s) * a.ldy + t0 + tt] = v;
             }
         }
         if (delay && !a.warmup) {
             __syncthreads();                   // this chunk's pre_d is visible CTA-wide (L2 reads below)
-            for (int idx = tid; idx < S * CH; idx += 128) {
+            for (int idx = tid; idx < SC * CH; idx += 128) {
                 const int s = idx / CH, tt = idx % CH;
                 if (s < ns && tt < n) {
                     const long long tg = t0 + tt;
@@ -336,8 +345,8 @@ __global__ void __launch_bounds__(128, FMT == FMT_TF32 ? 2 : 4) gru_mma_kernel(c
 #pragma unroll
         for (int u = 0; u < 2; ++u)
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int s = nt * 8 + 2 * tig + e;
+            for (int e = 0; e < NE; ++e) {
+                const int s = (nt * 8 + 2 * tig + e) / CS;
                 if (s < ns) a.h_out[(b0 + s) * 64 + u0 + u] = hst[nt][u][e];
             }
     if (delay) {
@@ -352,7 +361,7 @@ __global__ void __launch_bounds__(128, FMT == FMT_TF32 ? 2 : 4) gru_mma_kernel(c
     }
 }
 
-template <int FMT, int NT>
+template <int FMT, int NT, bool HALF>
 cudaError_t launch_mma_one(const GruArgs& a, cudaStream_t st)
 {
     using C = MmaCfg<FMT, NT>;
@@ -361,12 +370,13 @@ cudaError_t launch_mma_one(const GruArgs& a, cudaStream_t st)
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     if (dev < 64 && !configured[dev]) {
-        e = cudaFuncSetAttribute(gru_mma_kernel<FMT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+        e = cudaFuncSetAttribute(gru_mma_kernel<FMT, NT, HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
         if (e != cudaSuccess) return e;
         configured[dev] = true;
     }
-    const long long grid = (a.B + C::S - 1) / C::S;
-    gru_mma_kernel<FMT, NT><<<(unsigned)grid, 128, C::SMEM_BYTES, st>>>(a);
+    constexpr int SC = HALF ? 4 : C::S;
+    const long long grid = (a.B + SC - 1) / SC;
+    gru_mma_kernel<FMT, NT, HALF><<<(unsigned)grid, 128, C::SMEM_BYTES, st>>>(a);
     ++g_launches;
     return cudaGetLastError();
 }
@@ -374,13 +384,14 @@ cudaError_t launch_mma_one(const GruArgs& a, cudaStream_t st)
 template <int FMT>
 cudaError_t launch_mma_fmt(const GruArgs& a, int nt, cudaStream_t st)
 {
-    if (nt >= 2) return launch_mma_one<FMT, 2>(a, st);
-    return launch_mma_one<FMT, 1>(a, st);
+    if (nt >= 2) return launch_mma_one<FMT, 2, false>(a, st);
+    if (nt == 0) return launch_mma_one<FMT, 1, true>(a, st);
+    return launch_mma_one<FMT, 1, false>(a, st);
 }
 
 }  // namespace
 
-// fmt: FMT_F16 / FMT_BF16 / FMT_TF32.  n_tiles: 8-stream tiles per CTA (1 or 2).
+// fmt: FMT_F16 / FMT_BF16 / FMT_TF32.  n_tiles: 8-stream tiles per CTA (1 or 2); 0 = four streams per CTA (HALF).
 cudaError_t launch_gru_mma(const GruArgs& a, int fmt, int n_tiles, cudaStream_t st)
 {
     if (a.B <= 0 || a.T <= 0) return cudaSuccess;

@@ -49,9 +49,10 @@ def test_mode_mask():
         m.predict(torch.zeros(1, 1, 64, device=DEV))
 
 
-# kernel selectors (ntm_set_tuning): (n, 1|2) weight-stationary tcgen05 kernel, (n, 3) mma.sync kernel,
+# kernel selectors (ntm_set_tuning): (n, 1|2) weight-stationary tcgen05 kernel, (n, 3) mma.sync kernel with n = 4, 8, 16
+# streams per CTA,
 # (tiles, 4) stream-major tcgen05 kernel (f16/bf16 operands; tf32 falls through to mma.sync)
-@pytest.mark.parametrize("kernel", [(32, 2), (8, 3), (1, 4), (2, 4)])
+@pytest.mark.parametrize("kernel", [(32, 2), (8, 3), (4, 3), (1, 4), (2, 4)])
 @pytest.mark.parametrize("mode", TC_MODES)
 @pytest.mark.parametrize("tag", ["cfg1", "cfg2"])
 def test_tc_predict_esr_vs_golden(tag, mode, kernel):
@@ -95,7 +96,7 @@ def test_tc_batch_vs_oracle_and_launch_shapes(mode):
         # g = 1, 2: tcgen05 kernel (f16/bf16 operands; tf32 falls through to mma.sync) with n streams per group;
         # g = 3: warp-level mma.sync kernel with n streams per CTA
         fam = {}
-        for n, g in ((32, 1), (64, 1), (32, 2), (64, 2), (8, 3), (16, 3), (1, 4), (2, 4)):
+        for n, g in ((32, 1), (64, 1), (32, 2), (64, 2), (8, 3), (16, 3), (4, 3), (1, 4), (2, 4)):
             lib.load().ntm_set_tuning(n, g)
             y = m.predict(x)
             per_stream = ((y.cpu() - yr) ** 2).sum(2) / ((yr ** 2).sum(2) + 1e-5)
@@ -106,7 +107,7 @@ def test_tc_batch_vs_oracle_and_launch_shapes(mode):
                 assert float((m.predict(x[b:b + 1]) - y[b:b + 1]).abs().max()) <= 1e-6
 
 
-@pytest.mark.parametrize("kernel", [(0, 0), (32, 2), (64, 1), (8, 3), (1, 4), (2, 4)])
+@pytest.mark.parametrize("kernel", [(0, 0), (32, 2), (64, 1), (8, 3), (4, 3), (1, 4), (2, 4)])
 @pytest.mark.parametrize("mode", TC_MODES)
 def test_tc_segmentation_state_and_skip(mode, kernel):
     lib.load().ntm_set_tuning(*kernel)
@@ -129,7 +130,7 @@ def test_tc_segmentation_state_and_skip(mode, kernel):
         assert torch.equal(m.predict(view), m.predict(view.contiguous()))
 
 
-@pytest.mark.parametrize("kernel", [(32, 2), (8, 3)])
+@pytest.mark.parametrize("kernel", [(32, 2), (8, 3), (4, 3)])
 @pytest.mark.parametrize("mode", TC_MODES)
 def test_tc_diffdel(mode, kernel):
     lib.load().ntm_set_tuning(*kernel)
