@@ -60,41 +60,81 @@ __global__ void __launch_bounds__(32 * ESR_WARPS) esr_kernel(const float* __rest
         const double D32 = Dk[4] * Dk[4];
         double Dl = 1.0;                                          // D^lane
         for (int i = 0; i < lane; ++i) Dl *= D;
+        double Dm[5];                                             // scan multipliers, zero where the partner lane is out of range
+#pragma unroll
+        for (int k = 0; k < 5; ++k) Dm[k] = lane >= (1 << k) ? Dk[k] : 0.0;
         const double g = R - 1.0;
         double se_tile = 0.0, st_tile = 0.0;                      // S of e / of t at the sample before the tile
         const long long n0 = c0 >= ESR_WARM ? c0 - ESR_WARM : 0;
+        // raw samples of one tile: current and delayed-by-1999 values of t and o (zero outside [0, T))
+        auto fetch = [&](long long nb, float (&tv)[4], float (&ov)[4], float (&td)[4], float (&od)[4]) {
+            if (nb >= ESR_TAPS - 1 && nb + 128 <= T) {            // interior tile (warp-uniform): no bounds checks
+                const float* tp = t + nb + 4 * lane;
+                const float* op = o + nb + 4 * lane;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    tv[j] = __ldg(tp + j);
+                    ov[j] = __ldg(op + j);
+                    td[j] = __ldg(tp + j - (ESR_TAPS - 1));
+                    od[j] = __ldg(op + j - (ESR_TAPS - 1));
+                }
+                return;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const long long nn = nb + 4 * lane + j, nd = nn - (ESR_TAPS - 1);
+                const bool in = nn < T, ind = nd >= 0 && nd < T;
+                tv[j] = in ? __ldg(t + nn) : 0.0f;
+                ov[j] = in ? __ldg(o + nn) : 0.0f;
+                td[j] = ind ? __ldg(t + nd) : 0.0f;
+                od[j] = ind ? __ldg(o + nd) : 0.0f;
+            }
+        };
+        float ntv[4], nov[4], ntd[4], nod[4];
+        fetch(n0, ntv, nov, ntd, nod);
         for (long long nb = n0; nb < c1; nb += 128) {
             const long long n = nb + 4 * lane;
             double xe[4], xt[4], ue[4], ut[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const long long nn = n + j, nd = nn - (ESR_TAPS - 1);
-                const float tv = nn < T ? __ldg(t + nn) : 0.0f, ov = nn < T ? __ldg(o + nn) : 0.0f;
-                const float td = (nd >= 0 && nd < T) ? __ldg(t + nd) : 0.0f, od = (nd >= 0 && nd < T) ? __ldg(o + nd) : 0.0f;
-                xt[j] = (double)tv;
-                xe[j] = (double)tv - (double)ov;
-                ut[j] = fma(-Rw, (double)td, xt[j]);
-                ue[j] = fma(-Rw, (double)td - (double)od, xe[j]);
+                xt[j] = (double)ntv[j];
+                xe[j] = (double)ntv[j] - (double)nov[j];
+                ut[j] = fma(-Rw, (double)ntd[j], xt[j]);
+                ue[j] = fma(-Rw, (double)ntd[j] - (double)nod[j], xe[j]);
             }
+            // the next tile's loads are in flight while this one is scanned (the scan is a long dependent chain)
+            if (nb + 128 < c1) fetch(nb + 128, ntv, nov, ntd, nod);
             // lane aggregates from zero state, inclusive decayed scan over the lanes
             double ae = fma(fma(fma(ue[0], R, ue[1]), R, ue[2]), R, ue[3]);
             double at = fma(fma(fma(ut[0], R, ut[1]), R, ut[2]), R, ut[3]);
 #pragma unroll
             for (int k = 0; k < 5; ++k) {
                 const double pe = __shfl_up_sync(0xffffffffu, ae, 1 << k), pt = __shfl_up_sync(0xffffffffu, at, 1 << k);
-                if (lane >= (1 << k)) { ae = fma(Dk[k], pe, ae); at = fma(Dk[k], pt, at); }
+                ae = fma(Dm[k], pe, ae);
+                at = fma(Dm[k], pt, at);
             }
             double se = __shfl_up_sync(0xffffffffu, ae, 1), st = __shfl_up_sync(0xffffffffu, at, 1);
             if (lane == 0) { se = 0.0; st = 0.0; }
             se = fma(Dl, se_tile, se);                            // S at the sample before this lane's first
             st = fma(Dl, st_tile, st);
+            if (nb >= c0 && nb + 128 <= c1) {                     // tile entirely inside the chunk (warp-uniform)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const double fe = fma(g, se, xe[j]), ft = fma(g, st, xt[j]);
-                if (n + j >= c0 && n + j < c1) { num = fma(fe, fe, num); den = fma(ft, ft, den); }
-                se = fma(R, se, ue[j]);
-                st = fma(R, st, ut[j]);
-            }
+                for (int j = 0; j < 4; ++j) {
+                    const double fe = fma(g, se, xe[j]), ft = fma(g, st, xt[j]);
+                    num = fma(fe, fe, num);
+                    den = fma(ft, ft, den);
+                    se = fma(R, se, ue[j]);
+                    st = fma(R, st, ut[j]);
+                }
+            } else if (nb >= c0) {                                // the chunk's last, partial tile
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const double fe = fma(g, se, xe[j]), ft = fma(g, st, xt[j]);
+                    if (n + j < c1) { num = fma(fe, fe, num); den = fma(ft, ft, den); }
+                    se = fma(R, se, ue[j]);
+                    st = fma(R, st, ut[j]);
+                }
+            }                                                     // warm-up tiles only feed the carry below
             se_tile = fma(D32, se_tile, __shfl_sync(0xffffffffu, ae, 31));
             st_tile = fma(D32, st_tile, __shfl_sync(0xffffffffu, at, 31));
         }
