@@ -88,8 +88,9 @@ int run_gru(Handle* hd, int mode, const ntm::GruArgs& a, cudaStream_t st)
             CU(ntm::launch_gru_tcs(a, hd->tcs, fmt, hd->sm_count, tg == 4 ? (g_tune_s & 3) : 0, tg == 4 ? (g_tune_s >> 2) - 1 : -1, st));
             g_last_kernel = 3;
         } else if (use_mma) {
-            // tuning (n, 3): n = 4 / 8 / 16 streams per CTA; automatic: 4 while there are SMs to spare (shorter step)
-            const int nt = g_tune_s > 0 && tg == 3 ? g_tune_s / 8 : (a.B <= 4ll * hd->sm_count ? 0 : 1);
+            // tuning (n, 3): n = 4 / 8 / 16 streams per CTA; automatic: 4 (shorter dependent step) up to two such CTAs
+            // per SM -- measured 231 vs 241 ns/step at 1024 streams, 197 vs 245 at <= 592 (profiles/r01_mma_half_check.txt)
+            const int nt = g_tune_s > 0 && tg == 3 ? g_tune_s / 8 : (a.B <= 8ll * hd->sm_count ? 0 : 1);
             CU(ntm::launch_gru_mma(a, fmt, nt, st));
             g_last_kernel = 1;
         } else {

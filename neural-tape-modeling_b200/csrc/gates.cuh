@@ -57,6 +57,15 @@ __device__ __forceinline__ void gates_rz_dn_pre(float ar, float az, float an, fl
     dn = 1.0f + ex2_approx(fminf(fmaf(r, an, gin), EX2_CLAMP));
 }
 
+// Latency-regime form: r has its own reciprocal (r -> n -> h' is the step's critical path; sharing 1/(d_r d_z) makes r
+// wait for z's ex2 and two more multiplies), z's ex2 / rcp fill the MUFU pipe's idle slots.  5.5 MUFU per pair.
+__device__ __forceinline__ void gates_rz_dn_fast_r(const UnitConst& c, float ar, float az, float an, float x, float& z, float& dn)
+{
+    const float r = rcp_approx(1.0f + ex2_approx(ar + fmaf(c.cr_w, x, c.cr_b)));
+    dn = 1.0f + ex2_approx(fminf(fmaf(r, an + c.ch_b, fmaf(c.cn_w, x, c.cn_b)), EX2_CLAMP));
+    z = rcp_approx(1.0f + ex2_approx(az + fmaf(c.cz_w, x, c.cz_b)));
+}
+
 // new states of two pairs (their n-gate denominators share one reciprocal).  Only pair up the SAME stream (two hidden
 // units): a reciprocal shared between two streams would make a stream's rounding depend on its neighbour.
 __device__ __forceinline__ void gates_blend2(float z0, float dn0, float h0, float z1, float dn1, float h1, float& hn0, float& hn1)

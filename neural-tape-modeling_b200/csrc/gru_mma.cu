@@ -283,11 +283,17 @@ __global__ void __launch_bounds__(128, FMT == FMT_TF32 ? 2 : 4) gru_mma_kernel(c
                 for (int u = 0; u < 2; ++u)
 #pragma unroll
                     for (int e = 0; e < NE; ++e)
-                        gates_rz_dn(uc[u], acc[nt][u][e], acc[nt][u][2 + e], acc[nt][2][2 * u + e], e ? xv.y : xv.x,
+                        gates_rz_dn_fast_r(uc[u], acc[nt][u][e], acc[nt][u][2 + e], acc[nt][2][2 * u + e], e ? xv.y : xv.x,
                                     z[u][e], dn[u][e]);
 #pragma unroll
-                for (int e = 0; e < NE; ++e)       // the two hidden units of one stream share the n-gate reciprocal
-                    gates_blend2(z[0][e], dn[0][e], hst[nt][0][e], z[1][e], dn[1][e], hst[nt][1][e], hn[0][e], hn[1][e]);
+                for (int e = 0; e < NE; ++e) {
+                    if (HALF) {                    // MUFU slots to spare: own n-gate reciprocals, shorter dependent chain
+                        hn[0][e] = gates_blend1(z[0][e], dn[0][e], hst[nt][0][e]);
+                        hn[1][e] = gates_blend1(z[1][e], dn[1][e], hst[nt][1][e]);
+                    } else {                       // the two hidden units of one stream share the n-gate reciprocal
+                        gates_blend2(z[0][e], dn[0][e], hst[nt][0][e], z[1][e], dn[1][e], hst[nt][1][e], hn[0][e], hn[1][e]);
+                    }
+                }
 #pragma unroll
                 for (int e = 0; e < NE; ++e) {
                     hst[nt][0][e] = hn[0][e];

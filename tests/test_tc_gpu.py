@@ -101,7 +101,8 @@ def test_tc_batch_vs_oracle_and_launch_shapes(mode):
             y = m.predict(x)
             per_stream = ((y.cpu() - yr) ** 2).sum(2) / ((yr ** 2).sum(2) + 1e-5)
             assert float(per_stream.max()) <= ESR_TOL, (n, g)
-            first = fam.setdefault(g if g >= 3 or mode == "tf32" else 1, y)
+            # same kernel family and form: same arithmetic (the 4-streams-per-CTA form uses its own reciprocals)
+            first = fam.setdefault((g, n == 4) if g >= 3 or mode == "tf32" else 1, y)
             assert float((y - first).abs().max()) <= 1e-6, (n, g)      # same kernel family: same arithmetic
             for b in (0, 31, 76):
                 assert float((m.predict(x[b:b + 1]) - y[b:b + 1]).abs().max()) <= 1e-6

@@ -22,7 +22,7 @@ with torch.inference_mode():
         L.ntm_set_tuning(8, 3)
         m.initialize_hidden(); m.warm_start()
         hw = m.hidden.clone()
-        for B, T in ((1, 200000), (5, 100000), (256, 48000), (512, 48000), (592, 48000), (1024, 24000)):
+        for B, T in [(1, 200000), (256, 48000), (592, 48000), (1024, 24000), (1184, 24000), (1536, 24000), (2048, 24000), (4096, 12000)] if len(sys.argv) > 1 else ((1, 200000), (5, 100000), (256, 48000), (512, 48000), (592, 48000), (1024, 24000)):
             x = signals.stream_batch_device(B, T, dev, dur=10.0).reshape(B, 1, T)
             res = {}
             for tune in ((8, 3), (4, 3), (0, 0)):
