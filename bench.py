@@ -345,6 +345,26 @@ def aux_measurements(ntm_b200, signals, dev, mode):
             lat.append(time.perf_counter() - t1)
         lat.sort()
         out[f"batch1_block64_latency_us_median_{md}"] = lat[len(lat) // 2] * 1e6
+    # the same blocks through the RESIDENT server kernel (ntm_rt_*): host block in -> host block out, no launch per block
+    m1.mode = "f16"
+    m1.initialize_hidden(); m1.warm_start()
+    torch.cuda.synchronize(dev)
+    x1h = x1.cpu().reshape(1, -1)
+    hblocks = [x1h[:, 64 * k:64 * k + 64].contiguous() for k in range(nblk)]
+    rt = m1.realtime_stream(1, 64)
+    for k in range(50):
+        rt.process(hblocks[k])
+    lat = []
+    t0 = time.perf_counter()
+    for k in range(nblk):
+        t1 = time.perf_counter()
+        rt.process(hblocks[k])
+        lat.append(time.perf_counter() - t1)
+    out["batch1_block64_ns_per_sample_resident_server_f16"] = (time.perf_counter() - t0) * 1e9 / (nblk * 64)
+    lat.sort()
+    out["batch1_block64_latency_us_median_resident_server_f16"] = lat[len(lat) // 2] * 1e6
+    out["batch1_block64_latency_us_p99_resident_server_f16"] = lat[int(len(lat) * 0.99)] * 1e6
+    rt.close()
     m1.mode = "fp32"
     m1.initialize_hidden(); m1.warm_start()
     m1.mode = "f16"

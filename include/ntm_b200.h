@@ -40,6 +40,7 @@ extern "C" {
 #define NTM_EDELAY       (-5)   /* a delay value exceeds the history length D (the reference's assert,
                                    code/model.py:283) -- only returned by ntm_delay_check */
 #define NTM_ENODEVICE    (-6)   /* no CUDA device / not an sm_100 device */
+#define NTM_ECLOSED      (-7)   /* real-time stream: the resident kernel has left (closed or idle timeout) */
 
 /* arithmetic modes of the hidden-to-hidden contraction (gates, state and head are always fp32) */
 #define NTM_MODE_FP32     0     /* fp32 FFMA on CUDA cores, libm-grade activations: the parity anchor */
@@ -103,6 +104,22 @@ int ntm_delay_forward(const float* x, int64_t ldx, const float* d, int64_t ldd, 
 /* The reference's `assert self.max_delay >= torch.max(dt)` (code/model.py:283).  SYNCHRONISES the stream.
  * Returns NTM_EDELAY if any d[b][t] > D. */
 int ntm_delay_check(const float* d, int64_t ldd, int64_t B, int64_t T, int64_t D, int device, void* stream);
+
+/*
+ * Real-time block mode with a RESIDENT kernel (BASELINE cfg 5: consecutive RNN.forward calls on short blocks with the
+ * state carried, code/model.py:67-88 with self.hidden kept).  ntm_rt_open launches one persistent CTA that keeps the
+ * weights, the hidden state and its staging on chip and waits on a page-locked mailbox; ntm_rt_process hands it one block
+ * (x_host: B x block_len contiguous HOST floats) and returns when y_host is filled -- two PCIe round trips per block
+ * instead of a kernel launch, a prologue and a stream synchronisation.  ntm_rt_close stops the kernel and returns the
+ * final state.  B <= 4 streams, block_len <= 256, tensor-core modes only (NTM_EUNSUPPORTED for NTM_MODE_FP32).
+ * h_host: B x 64 initial state or NULL (zeros).  The kernel leaves by itself after idle_timeout_ms without a block
+ * (ntm_rt_process then returns NTM_ECLOSED).  While a stream is open, do NOT synchronise the whole device
+ * (cudaDeviceSynchronize, cudaFree): the resident kernel only ends at close / idle timeout.  One thread per stream.
+ */
+int ntm_rt_open(void* handle, int mode, const float* h_host, int64_t B, int64_t block_len, int skip,
+                int idle_timeout_ms, void** rt);
+int ntm_rt_process(void* rt, const float* x_host, float* y_host);
+int ntm_rt_close(void* rt, float* h_host_out);
 
 /*
  * Evaluation losses on the device (the step right after the recurrent path, code/test-model.py:250-253,386-388).

@@ -2,6 +2,6 @@
 (GRU-HS[64] tape nonlinearity, DiffDelGRU delay line).  See DESIGN.md."""
 from . import lib, sharding, signals  # noqa: F401
 from .losses import DCPreESR, ESRLoss  # noqa: F401
-from .model import RNN, BlockStream, DiffDelRNN, TimeVaryingDelayLine  # noqa: F401
+from .model import RNN, BlockStream, DiffDelRNN, RealtimeStream, TimeVaryingDelayLine  # noqa: F401
 
-__all__ = ["RNN", "BlockStream", "DiffDelRNN", "TimeVaryingDelayLine", "ESRLoss", "DCPreESR", "lib", "sharding", "signals"]
+__all__ = ["RNN", "BlockStream", "RealtimeStream", "DiffDelRNN", "TimeVaryingDelayLine", "ESRLoss", "DCPreESR", "lib", "sharding", "signals"]

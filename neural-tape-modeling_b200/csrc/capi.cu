@@ -2,6 +2,7 @@
 // No torch types, no exceptions, no hidden allocation on the device-pointer entry points.
 #include <new>
 #include <string.h>
+#include <time.h>
 
 #include "../../include/ntm_b200.h"
 #include "ntm_common.cuh"
@@ -249,6 +250,7 @@ const char* ntm_strerror(int code)
         case NTM_ECUDA: return cudaGetErrorString((cudaError_t)t_last_cuda);
         case NTM_EDELAY: return "delay exceeds max_delay (history length)";
         case NTM_ENODEVICE: return "no usable CUDA device (sm_100 required)";
+        case NTM_ECLOSED: return "real-time stream is closed (stopped or idle timeout)";
         default: return "unknown error";
     }
 }
@@ -414,6 +416,126 @@ int ntm_delay_check(const float* d, int64_t ldd, int64_t B, int64_t T, int64_t D
     cudaFree(flag);
     if (e != cudaSuccess) return cuda_fail(e);
     return host_flag ? NTM_EDELAY : NTM_OK;
+}
+
+// ---- real-time streams: a resident server kernel fed through a mapped host mailbox --------------------------------
+}  // extern "C"
+
+namespace {
+
+constexpr unsigned RT_MAGIC = 0x4e545254u;   // "NTRT"
+struct RtStream {
+    unsigned magic;
+    Handle* hd;
+    int B, T;
+    ntm::RtMailbox* mb;       // page-locked, mapped
+    float* h_dev;             // B x 64 state, read at open, written when the server leaves
+    cudaStream_t st;
+    unsigned seq;
+    bool dead;                // the server left (stop, idle timeout or error)
+};
+RtStream* as_rt(void* p)
+{
+    RtStream* r = static_cast<RtStream*>(p);
+    return (r && r->magic == RT_MAGIC) ? r : nullptr;
+}
+double now_s()
+{
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+void rt_free(RtStream* r)
+{
+    if (r->st) cudaStreamDestroy(r->st);
+    if (r->h_dev) cudaFree(r->h_dev);
+    if (r->mb) cudaFreeHost(r->mb);
+    r->magic = 0;
+    delete r;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ntm_rt_open(void* handle, int mode, const float* h_host, int64_t B, int64_t block_len, int skip, int idle_timeout_ms,
+                void** rt)
+{
+    if (!rt) return NTM_EINVAL;
+    *rt = nullptr;
+    Handle* hd = as_handle(handle);
+    if (!hd || B < 1 || B > ntm::RT_MAXSTREAMS || block_len < 1 || block_len > ntm::RT_MAXBLK || idle_timeout_ms < 1)
+        return NTM_EINVAL;
+    if (!mode_supported(mode) || mode == NTM_MODE_FP32) return NTM_EUNSUPPORTED;     // the server is the mma.sync kernel
+    DeviceGuard g(hd->device);
+    if (!g.ok) return cuda_fail(cudaErrorInvalidDevice);
+    RtStream* r = new (std::nothrow) RtStream();
+    if (!r) return NTM_ENOMEM;
+    r->magic = RT_MAGIC; r->hd = hd; r->B = (int)B; r->T = (int)block_len; r->mb = nullptr; r->h_dev = nullptr;
+    r->st = nullptr; r->seq = 0; r->dead = false;
+    cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&r->mb), sizeof(ntm::RtMailbox), cudaHostAllocMapped);
+    if (e == cudaSuccess) {
+        memset(r->mb, 0, sizeof(ntm::RtMailbox));
+        e = cudaMalloc(&r->h_dev, sizeof(float) * 64 * (size_t)B);
+    }
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&r->st, cudaStreamNonBlocking);
+    if (e == cudaSuccess)
+        e = h_host ? cudaMemcpyAsync(r->h_dev, h_host, sizeof(float) * 64 * (size_t)B, cudaMemcpyHostToDevice, r->st)
+                   : cudaMemsetAsync(r->h_dev, 0, sizeof(float) * 64 * (size_t)B, r->st);
+    ntm::RtMailbox* mb_dev = nullptr;
+    if (e == cudaSuccess) e = cudaHostGetDevicePointer(reinterpret_cast<void**>(&mb_dev), r->mb, 0);
+    if (e == cudaSuccess) {
+        ntm::GruArgs a{};
+        a.blob = hd->blob; a.x = &mb_dev->x[0][0]; a.y = &mb_dev->y[0][0]; a.h_in = r->h_dev; a.h_out = r->h_dev;
+        a.B = B; a.T = block_len; a.ldx = ntm::RT_MAXBLK; a.ldy = ntm::RT_MAXBLK; a.skip = skip;
+        a.rt = mb_dev; a.rt_idle_ns = (unsigned long long)idle_timeout_ms * 1000000ull;
+        const int fmt = mode == NTM_MODE_TF32 ? 2 : mode == NTM_MODE_BF16 ? 1 : 0;
+        e = ntm::launch_gru_mma_rt(a, fmt, r->st);
+    }
+    if (e != cudaSuccess) { rt_free(r); return cuda_fail(e); }
+    *rt = r;
+    return NTM_OK;
+}
+
+int ntm_rt_process(void* rt, const float* x_host, float* y_host)
+{
+    RtStream* r = as_rt(rt);
+    if (!r || !x_host || !y_host) return NTM_EINVAL;
+    if (r->dead) return NTM_ECLOSED;
+    ntm::RtMailbox* mb = r->mb;
+    for (int s = 0; s < r->B; ++s) memcpy(&mb->x[s][0], x_host + (size_t)s * r->T, sizeof(float) * (size_t)r->T);
+    __atomic_thread_fence(__ATOMIC_SEQ_CST);            // the block is in memory before its sequence number
+    const unsigned seq = ++r->seq;
+    mb->seq_in = seq;
+    const double t0 = now_s();
+    unsigned spins = 0;
+    while (mb->seq_out != seq) {
+        if ((++spins & 0xfff) == 0 && now_s() - t0 > 0.05) {
+            // slow path: has the server left (idle timeout, error)?
+            const cudaError_t q = cudaStreamQuery(r->st);
+            if (q != cudaErrorNotReady) {
+                r->dead = true;
+                return q == cudaSuccess ? NTM_ECLOSED : cuda_fail(q);
+            }
+            if (now_s() - t0 > 10.0) { r->dead = true; return NTM_ECLOSED; }
+        }
+    }
+    __atomic_thread_fence(__ATOMIC_SEQ_CST);
+    for (int s = 0; s < r->B; ++s) memcpy(y_host + (size_t)s * r->T, &mb->y[s][0], sizeof(float) * (size_t)r->T);
+    return NTM_OK;
+}
+
+int ntm_rt_close(void* rt, float* h_host_out)
+{
+    RtStream* r = as_rt(rt);
+    if (!r) return NTM_EINVAL;
+    DeviceGuard g(r->hd->device);
+    r->mb->seq_in = ntm::RT_STOP;
+    cudaError_t e = cudaStreamSynchronize(r->st);        // the server writes the final state on its way out
+    if (e == cudaSuccess && h_host_out)
+        e = cudaMemcpy(h_host_out, r->h_dev, sizeof(float) * 64 * (size_t)r->B, cudaMemcpyDeviceToHost);
+    rt_free(r);
+    return e == cudaSuccess ? NTM_OK : cuda_fail(e);
 }
 
 int ntm_esr_sums(const float* out, int64_t ldo, const float* target, int64_t ldt, int64_t B, int64_t T, int dc_pre,

@@ -90,10 +90,14 @@ struct MmaCfg {
 // HALF (NT == 1 only): the CTA owns 4 streams, placed in the EVEN columns of its n8 tile (stream s <-> column 2s), and
 // skips the gate math, state stores and outputs of the odd columns: half the MUFU / FMA work per step for the same
 // MMAs -- the shorter dependent step wins whenever there are CTAs to spare (B <= 4 streams per SM: cfg 3, cfg 5).
-template <int FMT, int NT, bool HALF>
+// RT (HALF only): resident real-time server -- the CTA stays on its SM, keeps weights, state and staging on chip and
+// processes one block of a.T samples per mailbox hand-shake (a.rt, mapped host memory; a.x / a.y point into it), so a block
+// costs two PCIe round trips instead of a kernel launch, a prologue and a stream synchronisation.
+template <int FMT, int NT, bool HALF, bool RT = false>
 __global__ void __launch_bounds__(128, FMT == FMT_TF32 ? 2 : 4) gru_mma_kernel(const GruArgs a)
 {
     static_assert(!HALF || NT == 1, "HALF needs a single n8 tile");
+    static_assert(!RT || HALF, "the real-time server uses the 4-streams-per-CTA form");
     constexpr int SC = HALF ? 4 : 8 * NT;            // streams per CTA
     constexpr int CS = HALF ? 2 : 1;                 // column stride of a stream
     constexpr int NE = HALF ? 1 : 2;                 // live columns per thread and n8 tile
@@ -205,6 +209,8 @@ __global__ void __launch_bounds__(128, FMT == FMT_TF32 ? 2 : 4) gru_mma_kernel(c
         }
     };
 
+    __shared__ __align__(16) float rt_xblk[RT ? RT_MAXSTREAMS * RT_MAXBLK : 4];   // server form: one block of x ...
+    __shared__ __align__(16) float rt_yblk[RT ? RT_MAXSTREAMS * RT_MAXBLK : 4];   // ... and of y, staged on chip
     const bool delay = a.d != nullptr;
     float* __restrict__ head_out = delay ? a.pre : a.y;
     const long long ldo = delay ? a.ldp : a.ldy;
@@ -214,8 +220,13 @@ __global__ void __launch_bounds__(128, FMT == FMT_TF32 ? 2 : 4) gru_mma_kernel(c
         float* dstb = xs + buf * CH * S;
         for (int idx = tid; idx < CH * S; idx += 128) {
             const int col = idx % S, tt = idx / S, s = col / CS;
-            if (col % CS == 0 && s < ns && tt < n) cp_async4(dstb + tt * S + col, a.x + (b0 + s) * a.ldx + t0 + tt);
-            else dstb[tt * S + col] = 0.0f;
+            if (col % CS == 0 && s < ns && tt < n) {
+                // (server form: the whole block was fetched into shared memory in one PCIe round trip)
+                if (RT) dstb[tt * S + col] = rt_xblk[s * RT_MAXBLK + t0 + tt];
+                else cp_async4(dstb + tt * S + col, a.x + (b0 + s) * a.ldx + t0 + tt);
+            } else {
+                dstb[tt * S + col] = 0.0f;
+            }
         }
         cp_async_commit();
     };
@@ -233,10 +244,45 @@ __global__ void __launch_bounds__(128, FMT == FMT_TF32 ? 2 : 4) gru_mma_kernel(c
             store_state2<FMT>(hb + col * F::ROW_BYTES, u0, hst[nt][0][e], hst[nt][1][e]);
             store_state2<FMT>(hb + C::HB_BYTES + col * F::ROW_BYTES, u0, 0.0f, 0.0f);     // dead columns stay finite
         }
-    load_x(0, 0);
-
     const long long nchunks = (a.T + CH - 1) / CH;
     int cur = 0;
+    unsigned rt_seen = 0;
+    __shared__ unsigned rt_flag;
+    do {
+    if (RT) {
+        // wait for the host to publish the next block (one uncached read of mapped host memory per poll)
+        if (tid == 0) {
+            unsigned long long t_wait;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_wait));
+            unsigned sq;
+            while ((sq = a.rt->seq_in) == rt_seen) {
+                unsigned long long now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (now - t_wait > a.rt_idle_ns) { sq = RT_STOP; break; }
+            }
+            rt_flag = sq;
+        }
+        __syncthreads();
+        if (rt_flag == RT_STOP) break;
+        rt_seen = rt_flag;
+        // fetch the block: every thread keeps up to 8 uncached loads of mapped host memory in flight (one round trip)
+        {
+            const int total = ns * (int)a.T;
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int idx = tid + 128 * i;
+                v[i] = idx < total ? __ldcv(a.x + (idx / (int)a.T) * a.ldx + idx % (int)a.T) : 0.0f;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int idx = tid + 128 * i;
+                if (idx < total) rt_xblk[(idx / (int)a.T) * RT_MAXBLK + idx % (int)a.T] = v[i];
+            }
+        }
+        __syncthreads();
+    }
+    load_x(0, 0);
     for (long long c = 0; c < nchunks; ++c) {
         const long long t0 = c * CH;
         const int n = (int)((a.T - t0) < (long long)CH ? (a.T - t0) : (long long)CH);
@@ -325,7 +371,8 @@ __global__ void __launch_bounds__(128, FMT == FMT_TF32 ? 2 : 4) gru_mma_kernel(c
                 float v = yp[tt * C::YP_LD + col] + yp[(CH + tt) * C::YP_LD + col] + yp[(2 * CH + tt) * C::YP_LD + col] +
                           yp[(3 * CH + tt) * C::YP_LD + col] + bo;
                 if (a.skip) v += xcur[tt * S + col];
-                head_out[(b0 + s) * ldo + t0 + tt] = v;
+                if (RT) rt_yblk[s * RT_MAXBLK + t0 + tt] = v;
+                else head_out[(b0 + s) * ldo + t0 + tt] = v;
                 if (delay && a.warmup) a.y[(b0 + s) * a.ldy + t0 + tt] = v;
             }
         }
@@ -344,6 +391,19 @@ __global__ void __launch_bounds__(128, FMT == FMT_TF32 ? 2 : 4) gru_mma_kernel(c
             }
         }
     }
+
+    if (RT) {
+        __syncthreads();
+        // the block's output goes out in full 128-byte lines (a warp writes 32 consecutive samples of one stream)
+        for (int idx = tid; idx < ns * RT_MAXBLK; idx += 128) {
+            const int sidx = idx / RT_MAXBLK, t = idx % RT_MAXBLK;
+            if (t < (int)a.T) a.y[sidx * a.ldy + t] = rt_yblk[sidx * RT_MAXBLK + t];
+        }
+        __threadfence_system();                // this block's y is visible to the host ...
+        __syncthreads();
+        if (tid == 0) a.rt->seq_out = rt_seen; // ... before its sequence number is
+    }
+    } while (RT);
 
     // ---- final state; rolled delay history (code/model.py:314-315) -------------------------------------------------
 #pragma unroll
@@ -388,6 +448,18 @@ cudaError_t launch_mma_one(const GruArgs& a, cudaStream_t st)
 }
 
 template <int FMT>
+cudaError_t launch_mma_rt_fmt(const GruArgs& a, cudaStream_t st)
+{
+    using C = MmaCfg<FMT, 1>;
+    cudaError_t e = cudaFuncSetAttribute(gru_mma_kernel<FMT, 1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         C::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    gru_mma_kernel<FMT, 1, true, true><<<1, 128, C::SMEM_BYTES, st>>>(a);
+    ++g_launches;
+    return cudaGetLastError();
+}
+
+template <int FMT>
 cudaError_t launch_mma_fmt(const GruArgs& a, int nt, cudaStream_t st)
 {
     if (nt >= 2) return launch_mma_one<FMT, 2, false>(a, st);
@@ -405,6 +477,17 @@ cudaError_t launch_gru_mma(const GruArgs& a, int fmt, int n_tiles, cudaStream_t 
         case FMT_TF32: return launch_mma_fmt<FMT_TF32>(a, n_tiles, st);
         case FMT_BF16: return launch_mma_fmt<FMT_BF16>(a, n_tiles, st);
         default: return launch_mma_fmt<FMT_F16>(a, n_tiles, st);
+    }
+}
+
+// The resident real-time server (one CTA, <= 4 streams, blocks of a.T <= RT_MAXBLK samples; see RtMailbox).
+cudaError_t launch_gru_mma_rt(const GruArgs& a, int fmt, cudaStream_t st)
+{
+    if (a.B <= 0 || a.B > RT_MAXSTREAMS || a.T <= 0 || a.T > RT_MAXBLK || !a.rt || a.d) return cudaErrorInvalidValue;
+    switch (fmt) {
+        case FMT_TF32: return launch_mma_rt_fmt<FMT_TF32>(a, st);
+        case FMT_BF16: return launch_mma_rt_fmt<FMT_BF16>(a, st);
+        default: return launch_mma_rt_fmt<FMT_F16>(a, st);
     }
 }
 

@@ -26,6 +26,21 @@ struct BlobLayout {
 };
 static_assert(BlobLayout::FP32_END % 4 == 0, "tensor-core images must stay 16-byte aligned");
 
+// Mailbox of a real-time stream (ntm_rt_*): page-locked, mapped host memory shared by the host thread and the resident
+// server kernel (gru_mma.cu, RT form).  The host writes a block into x, then bumps seq_in; the kernel writes y, then sets
+// seq_out = seq_in.  seq_in == RT_STOP ends the kernel.
+constexpr int RT_MAXBLK = 256;          // samples per block, at most
+constexpr int RT_MAXSTREAMS = 4;
+constexpr unsigned RT_STOP = 0xffffffffu;
+struct RtMailbox {
+    volatile unsigned seq_in;
+    unsigned pad0[31];
+    float x[RT_MAXSTREAMS][RT_MAXBLK];
+    volatile unsigned seq_out;
+    unsigned pad1[31];
+    float y[RT_MAXSTREAMS][RT_MAXBLK];
+};
+
 // Arguments of one recurrent launch; d == nullptr selects the plain RNN.forward path.
 struct GruArgs {
     const float* blob;
@@ -41,6 +56,8 @@ struct GruArgs {
     int D;
     int warmup;
     int skip;
+    RtMailbox* rt;                  // real-time server form only (x, y point into it)
+    unsigned long long rt_idle_ns;  // the server leaves after this long without a block
 };
 
 // Warp-uniform per-unit constants of the stream-major tcgen05 kernel (gru_tcs.cu); passed as a kernel parameter so
@@ -58,6 +75,7 @@ cudaError_t launch_gru_tc(const GruArgs& a, int fmt, int sm_count, int tune_n, i
 cudaError_t launch_gru_tcs(const GruArgs& a, const TcsConsts& kc, int fmt, int sm_count, int tiles, int var, cudaStream_t st);
 void fill_tcs_consts(const float* blob_host, TcsConsts* kc);
 cudaError_t launch_gru_mma(const GruArgs& a, int fmt, int n_tiles, cudaStream_t st);
+cudaError_t launch_gru_mma_rt(const GruArgs& a, int fmt, cudaStream_t st);    // resident real-time server, <= 4 streams
 void pack_tc_images(float* blob_host);   // host: fills BlobLayout::IMG_* from the fp32 part of the blob
 cudaError_t launch_delay(const float* x, long long ldx, const float* d, long long ldd, float* y, long long ldy,
                          const float* hist_in, float* hist_out, long long B, long long T, long long D, int warmup,

@@ -14,6 +14,7 @@ Q_VERSION, Q_DEVICE_COUNT, Q_SM_COUNT, Q_MODE_MASK, Q_KERNEL_LAUNCHES, Q_LAST_KE
 KERNEL_NAMES = {0: "gru_fp32_kernel (CUDA-core FFMA)", 1: "gru_mma_kernel (warp-level mma.sync)", 2: "gru_tc_kernel (tcgen05 + TMEM, weight-stationary)",
                 3: "gru_tcs_kernel (tcgen05 + TMEM, stream-major)"}
 E_DELAY = -5
+E_CLOSED = -7
 
 _vp = ctypes.c_void_p
 _i64 = ctypes.c_int64
@@ -34,6 +35,9 @@ SIGNATURES = {
     "ntm_gru_predict_host": (_int, [_vp, _int, _vp, _vp, _vp, _i64, _i64, _int, _i64]),
     "ntm_diffdel_predict_host": (_int, [_vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _i64]),
     "ntm_set_tuning": (_int, [_int, _int]),
+    "ntm_rt_open": (_int, [_vp, _int, _vp, _i64, _i64, _int, _int, ctypes.POINTER(_vp)]),
+    "ntm_rt_process": (_int, [_vp, _vp, _vp]),
+    "ntm_rt_close": (_int, [_vp, _vp]),
     "ntm_esr_sums": (_int, [_vp, _i64, _vp, _i64, _i64, _i64, _int, _vp, _int, _vp]),
 }
 

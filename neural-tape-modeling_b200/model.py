@@ -182,6 +182,10 @@ class RNN(torch.nn.Module):
         with the per-call host work stripped to one C call -- see BlockStream."""
         return BlockStream(self, n_streams, block_len)
 
+    def realtime_stream(self, n_streams=1, block_len=64, idle_timeout_ms=5000):
+        """Real-time block mode with a resident kernel (host blocks in, host blocks out) -- see RealtimeStream."""
+        return RealtimeStream(self, n_streams, block_len, idle_timeout_ms)
+
     def predict(self, input):
         """Zero state -> warm start -> whole signal (code/model.py:218-246), for any number of streams."""
         dev = self._device()
@@ -257,6 +261,73 @@ class BlockStream:
         """Hand the carried state back to the model (`model.hidden`)."""
         self.model.hidden = self.h
         return self.model.hidden
+
+
+class RealtimeStream:
+    """Block-by-block processing of up to 4 streams through a RESIDENT server kernel (ntm_rt_*, csrc/gru_mma.cu RT form).
+
+    Same semantics as BlockStream / repeated `model(x_block)` calls with carried `self.hidden` (code/model.py:67-88), but
+    blocks live in HOST memory (a real-time audio callback): `process(x)` takes a float32 host tensor or numpy array of
+    shape (n_streams, block_len) [or (n_streams, 1, block_len)] and returns the output block as a host tensor of the same
+    shape.  A block costs two PCIe round trips plus the kernel's own steps -- no launch, no prologue, no stream
+    synchronisation.  The state starts from `model.hidden` and is handed back by `close()`.  Tensor-core modes only.
+    While the stream is open do not synchronise the whole device (torch.cuda.synchronize()): the resident kernel only
+    ends at `close()` or after `idle_timeout_ms` without a block."""
+
+    def __init__(self, model, n_streams=1, block_len=64, idle_timeout_ms=5000):
+        dev = model._device()
+        if dev.type != "cuda":
+            raise RuntimeError("ntm_b200 has no CPU path; move the model to a CUDA device")
+        self.model, self.B, self.T, self.device = model, int(n_streams), int(block_len), dev
+        h = model._hidden_in(self.B, dev)
+        h_host = None if h is None else h.reshape(self.B, model.hidden_size).to("cpu", torch.float32).contiguous()
+        torch.cuda.current_stream(dev).synchronize()         # the state above is final before the server reads its copy
+        self._rt = ctypes.c_void_p()
+        rc = _lib.load().ntm_rt_open(model._handle(dev), _lib.MODES[model.mode], _ptr(h_host), self.B, self.T,
+                                     int(bool(model.skip)), int(idle_timeout_ms), ctypes.byref(self._rt))
+        _lib.check(rc)
+        self._y = torch.empty((self.B, self.T), dtype=torch.float32)
+        self._fn = _lib.load().ntm_rt_process
+        self._yp = ctypes.c_void_p(self._y.data_ptr())
+        self.x_in = torch.zeros((self.B, self.T), dtype=torch.float32)       # optional fixed input block for step()
+        self._xp = ctypes.c_void_p(self.x_in.data_ptr())
+
+    def step(self):
+        """Lowest-overhead form: process the block the caller wrote into `self.x_in`; returns the internal output
+        block (overwritten by the next call)."""
+        rc = self._fn(self._rt, self._xp, self._yp)
+        if rc:
+            _lib.check(rc)
+        return self._y
+
+    def process(self, x):
+        if self._rt is None:
+            raise RuntimeError("ntm_b200: real-time stream is closed")
+        xt = torch.as_tensor(x)
+        if xt.is_cuda or xt.dtype != torch.float32 or xt.numel() != self.B * self.T or not xt.is_contiguous():
+            raise RuntimeError(f"expected a contiguous float32 HOST block of {self.B} x {self.T} samples")
+        rc = self._fn(self._rt, ctypes.c_void_p(xt.data_ptr()), self._yp)
+        if rc:
+            _lib.check(rc)
+        return self._y.reshape(xt.shape)
+
+    def close(self):
+        """Stop the resident kernel and hand the carried state back to the model (`model.hidden`)."""
+        if self._rt is None:
+            return self.model.hidden
+        h = torch.empty((self.B, self.model.hidden_size), dtype=torch.float32)
+        rt, self._rt = self._rt, None
+        _lib.check(_lib.load().ntm_rt_close(rt, _ptr(h)))
+        self.model.hidden = h.reshape(1, self.B, self.model.hidden_size).to(self.device)
+        return self.model.hidden
+
+    def __del__(self):
+        try:
+            if getattr(self, "_rt", None) is not None:
+                _lib.load().ntm_rt_close(self._rt, None)
+                self._rt = None
+        except Exception:
+            pass
 
 
 class TimeVaryingDelayLine(torch.nn.Module):
