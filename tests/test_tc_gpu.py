@@ -250,3 +250,30 @@ def test_stream_major_dynamic_schedule_is_exact():
             assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
             assert bool(torch.isfinite(outs[0][0]).all())
             del x, outs
+
+
+def test_full_size_cfg2_properties():
+    """BASELINE config 2 at FULL size (1024 streams x 60 s = 2.95e9 samples, tensor-core mode, the bench workload) through
+    size-independent properties: causality / segmentation (the first second of the full run equals a one-second run, bit
+    for bit), stream independence (sampled streams re-run alone give the same samples), two sampled streams against the
+    host oracle over the first two seconds, everything finite, and the state equals the state of a chunked run."""
+    m = make_rnn("cfg2", "f16")
+    B, T, FS = 1024, 60 * 48000, 48000
+    x = signals.stream_batch_device(B, T, DEV, dur=60.0).reshape(B, 1, T)
+    with torch.inference_mode():
+        y = m.predict(x)
+        h_full = m.hidden.clone()
+        assert lib.query(lib.Q_LAST_KERNEL) == 1
+        assert bool(torch.isfinite(y[:, :, ::97]).all()) and bool(torch.isfinite(y[:, :, -4096:]).all())
+        y1 = m.predict(x[:, :, :FS])
+        assert torch.equal(y1, y[:, :, :FS])
+        # chunked continuation reproduces the tail and the final state
+        m.predict(x[:, :, :T - 3 * FS])
+        tail = m(x[:, :, T - 3 * FS:])
+        assert torch.equal(tail, y[:, :, T - 3 * FS:]) and torch.equal(m.hidden, h_full)
+        pick = [0, 517, 1023]
+        for b in pick:                                   # a stream alone (same 4-per-CTA form) == the stream in the batch
+            assert torch.equal(m.predict(x[b:b + 1, :, :2 * FS]), y[b:b + 1, :, :2 * FS])
+        yr, _ = ref_torch.RefNet(load_ckpt("cfg2")).predict(x[pick, :, :2 * FS].cpu())
+        per_stream = ((y[pick, :, :2 * FS].cpu() - yr) ** 2).sum(2) / ((yr ** 2).sum(2) + 1e-5)
+        assert float(per_stream.max()) <= ESR_TOL
