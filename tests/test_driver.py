@@ -1,0 +1,89 @@
+"""Batched evaluation driver (neural-tape-modeling_b200/driver.py): .wav I/O on the CPU, batched prediction + losses on
+the GPU equal to the reference-style one-file-at-a-time loop."""
+import os
+import struct
+import wave
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_ckpt
+from ntm_b200 import DCPreESR, ESRLoss, RNN, driver, signals
+
+
+def test_wav_roundtrip_float32_stereo_and_segments(tmp_path):
+    rng = np.random.default_rng(0)
+    a = rng.standard_normal((2, 1000)).astype(np.float32) * 3.0          # float files are NOT clipped / normalised
+    p = str(tmp_path / "a.wav")
+    driver.write_wav(p, a, 44100)
+    info = driver.wav_info(p)
+    assert (info["fs"], info["channels"], info["frames"], info["format"], info["bits"]) == (44100, 2, 1000, 3, 32)
+    b, fs = driver.read_wav(p)
+    assert fs == 44100 and np.array_equal(a, b)
+    seg, _ = driver.read_wav(p, frame_offset=100, num_frames=250)
+    assert np.array_equal(seg, a[:, 100:350])
+    tail, _ = driver.read_wav(p, frame_offset=990, num_frames=500)
+    assert np.array_equal(tail, a[:, 990:])
+    driver.write_wav(p, a[0], 48000)                                      # mono from a 1-D array
+    m, fs = driver.read_wav(p)
+    assert fs == 48000 and m.shape == (1, 1000) and np.array_equal(m[0], a[0])
+
+
+def test_wav_reads_pcm_files(tmp_path):
+    p16 = str(tmp_path / "p16.wav")
+    v = (np.arange(-5, 5) * 3000).astype("<i2")
+    with wave.open(p16, "wb") as w:
+        w.setnchannels(1); w.setsampwidth(2); w.setframerate(8000); w.writeframes(v.tobytes())
+    a, fs = driver.read_wav(p16)
+    assert fs == 8000 and np.allclose(a[0], v.astype(np.float32) / 32768.0)
+    p24 = str(tmp_path / "p24.wav")
+    vals = np.array([0, 1, -1, 8388607, -8388608, 123456, -654321], dtype=np.int32)
+    raw = b"".join(struct.pack("<i", int(x))[:3] for x in vals)
+    with wave.open(p24, "wb") as w:
+        w.setnchannels(1); w.setsampwidth(3); w.setframerate(8000); w.writeframes(raw)
+    a, _ = driver.read_wav(p24)
+    assert np.allclose(a[0], vals.astype(np.float64) / 8388608.0)
+    bad = str(tmp_path / "bad.wav")
+    open(bad, "wb").write(b"RIFFxxxxWAVX")
+    with pytest.raises(ValueError):
+        driver.wav_info(bad)
+
+
+@pytest.mark.gpu
+def test_batched_evaluator_equals_one_file_at_a_time(tmp_path):
+    dev = "cuda:0"
+    m = RNN(1, 64, 1, False).to(dev)
+    m.load_state_dict(load_ckpt("cfg2"))
+    m.mode = "f16"
+    rng = np.random.default_rng(1)
+    lens = [5000, 7321, 2048, 9000, 1500, 6000, 4097]
+    x = signals.stream_batch(len(lens), max(lens), dur=1.0)
+    examples = []
+    for i, n in enumerate(lens):
+        xin = np.stack([x[i, :n], (np.arange(n) % 441 == 0).astype(np.float32)])       # audio + pulse track
+        tgt = np.stack([0.9 * x[i, :n] + 0.01 * rng.standard_normal(n).astype(np.float32), xin[1]])
+        pi, pt = str(tmp_path / f"in_{i}.wav"), str(tmp_path / f"tg_{i}.wav")
+        driver.write_wav(pi, xin, 44100)
+        driver.write_wav(pt, tgt, 44100)
+        examples.append({"input_file": pi, "target_file": pt})
+    examples.append({"input_file": examples[3]["input_file"], "target_file": examples[3]["target_file"],
+                     "offset": 1000, "length": 3000})                                   # a dataset-style segment
+    out_dir = str(tmp_path / "pred")
+    res = driver.BatchedEvaluator(m, max_streams=3).run(examples, out_dir=out_dir, init_len=1024)
+    assert len(res) == len(examples)
+    with torch.inference_mode():
+        for ex, r in zip(examples, res):
+            a, fs = driver.read_wav(ex["input_file"], ex.get("offset", 0), ex.get("length", -1))
+            t, _ = driver.read_wav(ex["target_file"], ex.get("offset", 0), ex.get("length", -1))
+            xi = torch.from_numpy(a[0]).to(dev).reshape(1, 1, -1)
+            y1 = m.predict(xi)                                                           # the reference's per-file call
+            yw, fs2 = driver.read_wav(r["output_file"])
+            assert fs2 == fs == 44100 and r["frames"] == a.shape[1]
+            assert np.array_equal(yw[0], y1.cpu().numpy().reshape(-1))                   # batch == one file at a time
+            td = torch.from_numpy(t[0]).to(dev).reshape(1, 1, -1)
+            # (the loss sums are accumulated with atomics: equal up to the order of double additions)
+            assert r["ESR"] == pytest.approx(float(ESRLoss()(y1[:, :, 1024:], td[:, :, 1024:])), rel=1e-6)
+            assert r["DCPreESR"] == pytest.approx(float(DCPreESR()(y1[:, :, 1024:], td[:, :, 1024:])), rel=1e-6)
+            assert np.isfinite(r["ESR"]) and r["ESR"] > 0.0 and np.isfinite(r["DCPreESR"])
+    assert res[-1]["input_name"].endswith("_[1000:4000].wav")
