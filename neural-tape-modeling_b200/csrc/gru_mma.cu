@@ -84,7 +84,8 @@ struct MmaCfg {
     static constexpr int OFF_HB = 0;                               // [2][S][ROW_BYTES]
     static constexpr int OFF_XS = (2 * HB_BYTES + 127) / 128 * 128;   // [2][CH][S] floats
     static constexpr int OFF_YP = OFF_XS + 2 * CH * S * 4;         // [4 warps][CH][YP_LD] floats
-    static constexpr int SMEM_BYTES = OFF_YP + 4 * CH * YP_LD * 4;
+    static constexpr int OFF_DS = (OFF_YP + 4 * CH * YP_LD * 4 + 15) / 16 * 16;   // [2][CH][S] delay trajectory (DiffDelRNN)
+    static constexpr int SMEM_BYTES = OFF_DS + 2 * CH * S * 4;                    // + the pre_d ring, sized at launch
 };
 
 // HALF (NT == 1 only): the CTA owns 4 streams, placed in the EVEN columns of its n8 tile (stream s <-> column 2s), and
@@ -108,6 +109,8 @@ __global__ void __launch_bounds__(128, FMT == FMT_TF32 ? 2 : 4) gru_mma_kernel(c
     uint8_t* const hb = smem + C::OFF_HB;
     float* const xs = reinterpret_cast<float*>(smem + C::OFF_XS);
     float* const yp = reinterpret_cast<float*>(smem + C::OFF_YP);
+    float* const ds = reinterpret_cast<float*>(smem + C::OFF_DS);
+    float* const ring = reinterpret_cast<float*>(smem + C::SMEM_BYTES);      // [SC][a.ring_len] when a.ring_len > 0
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int gid = lane >> 2, tig = lane & 3;
@@ -231,6 +234,25 @@ __global__ void __launch_bounds__(128, FMT == FMT_TF32 ? 2 : 4) gru_mma_kernel(c
         cp_async_commit();
     };
 
+    const int rmask = a.ring_len - 1;
+    const bool use_ring = delay && !a.warmup && a.ring_len > 0;
+    auto load_d = [&](int buf, long long t0) {               // the chunk's delay trajectory, staged like x
+        const int n = (int)((a.T - t0) < (long long)CH ? (a.T - t0) : (long long)CH);
+        float* dstb = ds + buf * CH * S;
+        for (int idx = tid; idx < CH * SC; idx += 128) {
+            const int s = idx % SC, tt = idx / SC;
+            if (s < ns && tt < n) cp_async4(dstb + tt * S + s, a.d + (b0 + s) * a.ldd + t0 + tt);
+        }
+        cp_async_commit();
+    };
+    if (use_ring) {                                          // carried history -> ring positions -D .. -1
+        for (long long idx = tid; idx < (long long)ns * a.D; idx += 128) {
+            const int s = (int)(idx / a.D);
+            const int i = (int)(idx % a.D);
+            ring[s * a.ring_len + ((i - a.D) & rmask)] = a.hist_in[(b0 + s) * (long long)a.D + i];
+        }
+    }
+
     // ---- initial state: fp32 in registers (hst[nt][unit][stream]), rounded copy into state tile 0 ---------------
     float hst[NT][2][2];
 #pragma unroll
@@ -283,6 +305,7 @@ __global__ void __launch_bounds__(128, FMT == FMT_TF32 ? 2 : 4) gru_mma_kernel(c
         __syncthreads();
     }
     load_x(0, 0);
+    if (use_ring) load_d(0, 0);
     for (long long c = 0; c < nchunks; ++c) {
         const long long t0 = c * CH;
         const int n = (int)((a.T - t0) < (long long)CH ? (a.T - t0) : (long long)CH);
@@ -290,7 +313,10 @@ __global__ void __launch_bounds__(128, FMT == FMT_TF32 ? 2 : 4) gru_mma_kernel(c
         const float* xcur = xs + xb * CH * S;
         cp_async_wait_all();
         __syncthreads();                       // xs[xb] landed; state tile `cur` complete; previous flush done
-        if (c + 1 < nchunks) load_x(xb ^ 1, t0 + CH);
+        if (c + 1 < nchunks) {
+            load_x(xb ^ 1, t0 + CH);
+            if (use_ring) load_d(xb ^ 1, t0 + CH);
+        }
 
         for (int tt = 0; tt < n; ++tt) {
             const uint8_t* hcur = hb + cur * C::HB_BYTES;
@@ -374,9 +400,24 @@ __global__ void __launch_bounds__(128, FMT == FMT_TF32 ? 2 : 4) gru_mma_kernel(c
                 if (RT) rt_yblk[s * RT_MAXBLK + t0 + tt] = v;
                 else head_out[(b0 + s) * ldo + t0 + tt] = v;
                 if (delay && a.warmup) a.y[(b0 + s) * a.ldy + t0 + tt] = v;
+                if (use_ring) ring[s * a.ring_len + ((int)(t0 + tt) & rmask)] = v;
             }
         }
-        if (delay && !a.warmup) {
+        if (use_ring) {
+            // delay taps from the on-chip ring (the last ring_len >= D + CH samples of pre_d, history included) and the
+            // staged trajectory: no L2 round trip of the samples this CTA has just produced
+            __syncthreads();
+            const float* dcur = ds + xb * CH * S;
+            for (int idx = tid; idx < SC * CH; idx += 128) {
+                const int s = idx / CH, tt = idx % CH;
+                if (s < ns && tt < n) {
+                    const long long tg = t0 + tt;
+                    const float* rrow = ring + s * a.ring_len;
+                    a.y[(b0 + s) * a.ldy + tg] =
+                        delay_read(dcur[tt * S + s], tg, a.D, [&](long long i) { return rrow[(int)i & rmask]; });
+                }
+            }
+        } else if (delay && !a.warmup) {
             __syncthreads();                   // this chunk's pre_d is visible CTA-wide (L2 reads below)
             for (int idx = tid; idx < SC * CH; idx += 128) {
                 const int s = idx / CH, tt = idx % CH;
@@ -436,13 +477,27 @@ cudaError_t launch_mma_one(const GruArgs& a, cudaStream_t st)
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     if (dev < 64 && !configured[dev]) {
-        e = cudaFuncSetAttribute(gru_mma_kernel<FMT, NT, HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+        e = cudaFuncSetAttribute(gru_mma_kernel<FMT, NT, HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 C::SMEM_BYTES + 48 * 1024);
         if (e != cudaSuccess) return e;
         configured[dev] = true;
     }
     constexpr int SC = HALF ? 4 : C::S;
     const long long grid = (a.B + SC - 1) / SC;
-    gru_mma_kernel<FMT, NT, HALF><<<(unsigned)grid, 128, C::SMEM_BYTES, st>>>(a);
+    // DiffDelRNN: keep the last D + CH samples of pre_d per stream on chip if they fit (<= 48 KB of ring per CTA, so that
+    // four CTAs still share an SM); longer histories read their taps back through L2
+    GruArgs b = a;
+    b.ring_len = 0;
+    int smem_bytes = C::SMEM_BYTES;
+    if (a.d != nullptr && !a.warmup) {
+        long long rl = 64;
+        while (rl < (long long)a.D + C::CH + 1) rl *= 2;
+        if (rl * SC * 4 <= 48 * 1024) {
+            b.ring_len = (int)rl;
+            smem_bytes += (int)(rl * SC * 4);
+        }
+    }
+    gru_mma_kernel<FMT, NT, HALF><<<(unsigned)grid, 128, smem_bytes, st>>>(b);
     ++g_launches;
     return cudaGetLastError();
 }

@@ -56,6 +56,8 @@ struct GruArgs {
     int D;
     int warmup;
     int skip;
+    int ring_len;                   // mma.sync kernel, DiffDelRNN: samples of pre_d kept per stream in shared memory
+                                    // (power of two >= D + chunk; 0: read the delay taps back through L2)
     RtMailbox* rt;                  // real-time server form only (x, y point into it)
     unsigned long long rt_idle_ns;  // the server leaves after this long without a block
 };

@@ -277,3 +277,36 @@ def test_full_size_cfg2_properties():
         yr, _ = ref_torch.RefNet(load_ckpt("cfg2")).predict(x[pick, :, :2 * FS].cpu())
         per_stream = ((y[pick, :, :2 * FS].cpu() - yr) ** 2).sum(2) / ((yr ** 2).sum(2) + 1e-5)
         assert float(per_stream.max()) <= ESR_TOL
+
+
+@pytest.mark.parametrize("max_delay", [100, 364, 2000, 6000])
+def test_tc_diffdel_delay_read_paths_bit_exact(max_delay):
+    """The fused delay read of the mma.sync kernel keeps the last D + 32 samples of pre_d per stream in shared memory
+    when they fit (D <= ~3000 for four streams per CTA) and reads its taps back through L2 otherwise: both paths must
+    reproduce the oracle's delay line bit for bit on the engine's own pre_d and warm history, across segment boundaries."""
+    m = DiffDelRNN(input_size=1, hidden_size=64, output_size=1, skip=False, max_delay=max_delay).to(DEV)
+    m.load_state_dict(load_ckpt("cfg3"))
+    m.mode = "f16"
+    B, T = 6, 9000
+    rng = np.random.default_rng(max_delay)
+    x = dev(signals.stream_batch(B, T)).reshape(B, 1, T)
+    dn = (0.5 * max_delay * (1.0 + 0.9 * np.sin(np.arange(T)[None, :] / 700.0 + rng.uniform(0, 6, (B, 1))))).astype(np.float32)
+    dn[:, ::50] = np.floor(dn[:, ::50])                   # integer delays too
+    dn[0, :10] = 0.0
+    d = dev(dn).reshape(B, 1, T)
+    with torch.inference_mode():
+        m.initialize_hidden(1, m.max_delay)                 # the reference's warm start is batch 1 (SURVEY 9.3 #3)
+        m.warm_start()
+        hist_w = m.diffdel.buffer.cpu().numpy().reshape(1, -1)
+        m.hidden = m.hidden.expand(1, B, 64).contiguous()
+        m.diffdel.buffer = m.diffdel.buffer.expand(B, 1, -1).contiguous()
+        ys, ps, s = [], [], 0
+        for n in (31, 4000, 1, 4968):
+            yy, pp = m(x[:, :, s:s + n], d[:, :, s:s + n])
+            ys.append(yy)
+            ps.append(pp)
+            s += n
+        y, pre = torch.cat(ys, 2).cpu().numpy().reshape(B, T), torch.cat(ps, 2).cpu().numpy().reshape(B, T)
+        yo, _ = c_oracle.delay_forward(pre, dn, np.repeat(hist_w, B, 0))
+        assert np.array_equal(yo, y)
+        assert np.all(np.isfinite(y))
