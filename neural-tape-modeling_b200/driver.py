@@ -7,6 +7,11 @@ causal, so trailing padding never changes a real sample --, predicted with predi
 1024-sample warm start), cut by INIT_LEN, scored on the device (ESR / DCPreESR) and optionally written back as float32
 .wav files.  The on-disk format is the reference's: float32 (or PCM) RIFF/WAVE, channel 0 = audio, channel 1 (if any) =
 the 100 Hz pulse track.  No soundfile / torchaudio needed.
+
+All three prediction modes of the reference's loss loop (code/test-model.py:346-368) are covered: plain GRU, DiffDelGRU
+with the example's delay trajectory (`meta['delay_trajectory'] * fs`, :349-352), and GRU followed by the stand-alone delay
+line (`ADD_DELAY`, `apply_delay`, :259-290,354-360).  Trajectories come from the dataset's `trajectory_*.npy` files (a
+pickled dict with key 'delay_trajectory' in seconds, code/utilities/utilities.py:273-284) or from an array in the example.
 """
 import os
 import struct
@@ -94,15 +99,41 @@ def write_wav(path, data, fs):
         f.write(payload)
 
 
+def read_trajectory(path, offset=0, length=-1):
+    """Delay trajectory in SECONDS for frames [offset, offset+length) of a file: `trajectory_*.npy` holds a pickled dict
+    {'delay_trajectory', 'input_peaks', 'output_peaks', ...} (code/utilities/utilities.py:273-284); a plain array file is
+    accepted too.  The slice is the reference's `T_delay[offset:end]` (code/dataset.py:383)."""
+    a = np.load(path, allow_pickle=True)
+    if a.dtype == object and a.ndim == 0:
+        a = a.item()["delay_trajectory"]
+    a = np.asarray(a, dtype=np.float64).reshape(-1)
+    end = len(a) if length is None or length < 0 else int(offset) + int(length)
+    return a[int(offset):end]
+
+
+def mean_losses(results, keys=("ESR", "DCPreESR")):
+    """Dataset mean of the per-example losses = the reference's `results_dict[key] / num_batches` with batch size 1
+    (code/test-model.py:385-397)."""
+    return {k: float(np.mean([r[k] for r in results])) for k in keys if results and all(k in r for r in results)}
+
+
 class BatchedEvaluator:
     """Predict (and score) many examples per launch.
 
     examples: dicts with 'input_file' and optionally 'target_file', 'offset' (frames, default 0), 'length' (frames,
-    default: to the end of the file) -- the fields of `AudioDataset.examples` (code/dataset.py:348-379).  `model` is an
-    ntm_b200.RNN on a CUDA device; `max_streams` examples are packed per launch."""
+    default: to the end of the file) -- the fields of `AudioDataset.examples` (code/dataset.py:348-379) -- and, for the
+    delay modes, 'delay_trajectory' (array, SECONDS, one value per frame of the segment) or 'trajectory_file'
+    (`trajectory_*.npy`, sliced with the example's offset / length).
+    `model` is an ntm_b200.RNN or DiffDelRNN on a CUDA device; `delay` is an optional stand-alone
+    ntm_b200.TimeVaryingDelayLine applied after a plain RNN (the reference's ADD_DELAY); `max_streams` examples are
+    packed per launch."""
 
-    def __init__(self, model, max_streams=1024):
-        self.model, self.max_streams = model, int(max_streams)
+    def __init__(self, model, max_streams=1024, delay=None):
+        from .model import DiffDelRNN
+        self.model, self.max_streams, self.delay = model, int(max_streams), delay
+        self.diffdel = isinstance(model, DiffDelRNN)
+        if self.diffdel and delay is not None:
+            raise ValueError("ADD_DELAY applies to the plain GRU only (code/test-model.py:354)")
         self.losses = {"ESR": ESRLoss(), "DCPreESR": DCPreESR(dc_pre=True)}
 
     @staticmethod
@@ -110,10 +141,32 @@ class BatchedEvaluator:
         a, fs = read_wav(ex[key], ex.get("offset", 0), ex.get("length", -1))
         return a[0], fs                                       # channel 0 = audio (channel 1 = pulse track)
 
-    def run(self, examples, out_dir=None, init_len=0):
+    @staticmethod
+    def _trajectory(ex, n, fs):
+        """The example's delay trajectory in SAMPLES (`meta['delay_trajectory'].float() * fs`, code/test-model.py:349-351,
+        356-358): float32 first, then scaled, like the reference."""
+        if "delay_trajectory" in ex:
+            t = np.asarray(ex["delay_trajectory"], dtype=np.float64).reshape(-1)
+        elif "trajectory_file" in ex:
+            t = read_trajectory(ex["trajectory_file"], ex.get("offset", 0), ex.get("length", -1))
+        else:
+            raise KeyError("a delay mode needs 'delay_trajectory' or 'trajectory_file' in every example")
+        if len(t) < n:
+            raise ValueError(f"delay trajectory has {len(t)} values for a segment of {n} frames")
+        return torch.from_numpy(t[:n].astype(np.float32)) * float(fs)
+
+    def _apply_delay(self, d, y):
+        """`apply_delay` (code/test-model.py:259-290): fresh zero history for every stream, then the delay line over the
+        whole signal (the reference walks 4096-sample chunks with a carried buffer; the kernel carries the same history
+        inside one call, so the result is identical)."""
+        self.delay.init_buffer(y.shape[0])
+        return self.delay(y, d)
+
+    def run(self, examples, out_dir=None, init_len=0, write_pre_d=False):
         """-> one dict per example: {'input_name', 'frames', 'fs', ['ESR', 'DCPreESR',] ['output_file']}; losses are
         computed after cutting the first `init_len` samples (INIT_LEN, code/test-model.py:323-325,367-370)."""
         dev = self.model._device()
+        need_d = self.diffdel or self.delay is not None
         results = []
         with torch.inference_mode():
             for b0 in range(0, len(examples), self.max_streams):
@@ -124,8 +177,21 @@ class BatchedEvaluator:
                 xh = torch.zeros((B, 1, Tmax), dtype=torch.float32, pin_memory=True)
                 for i, (a, _) in enumerate(loaded):
                     xh[i, 0, :lens[i]] = torch.from_numpy(a)
-                y = self.model.predict(xh.to(dev, non_blocking=True))
+                x = xh.to(dev, non_blocking=True)
+                pre = None
+                if need_d:                                   # zero delay over the padding: reads only what exists
+                    dh = torch.zeros((B, 1, Tmax), dtype=torch.float32, pin_memory=True)
+                    for i, ex in enumerate(group):
+                        dh[i, 0, :lens[i]] = self._trajectory(ex, lens[i], loaded[i][1])
+                    d = dh.to(dev, non_blocking=True)
+                if self.diffdel:
+                    y, pre = self.model.predict(x, d)
+                else:
+                    y = self.model.predict(x)
+                    if self.delay is not None:
+                        y = self._apply_delay(d, y)
                 yh = y.cpu() if out_dir is not None else None
+                ph = pre.cpu() if out_dir is not None and write_pre_d and pre is not None else None
                 for i, ex in enumerate(group):
                     name = os.path.basename(ex["input_file"])
                     off = ex.get("offset", 0)
@@ -142,5 +208,8 @@ class BatchedEvaluator:
                         os.makedirs(out_dir, exist_ok=True)
                         res["output_file"] = os.path.join(out_dir, f"{stem}_[{off}:{off + lens[i]}]_pred.wav")
                         write_wav(res["output_file"], yh[i, 0, :lens[i]].numpy(), loaded[i][1])
+                        if ph is not None:
+                            res["pre_d_file"] = os.path.join(out_dir, f"{stem}_[{off}:{off + lens[i]}]_pred_pre_d.wav")
+                            write_wav(res["pre_d_file"], ph[i, 0, :lens[i]].numpy(), loaded[i][1])
                     results.append(res)
         return results

@@ -6,7 +6,8 @@ import ctypes
 import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libntm_b200.so")
+# NTM_B200_LIB: developer override to A/B another BUILD of the same library (never a different implementation)
+LIB_PATH = os.environ.get("NTM_B200_LIB") or os.path.join(PKG, "libntm_b200.so")
 
 MODE_FP32, MODE_TF32, MODE_BF16, MODE_TF32X3, MODE_F16 = 0, 1, 2, 3, 4
 MODES = {"fp32": MODE_FP32, "tf32": MODE_TF32, "bf16": MODE_BF16, "tf32x3": MODE_TF32X3, "f16": MODE_F16}

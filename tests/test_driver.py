@@ -87,3 +87,90 @@ def test_batched_evaluator_equals_one_file_at_a_time(tmp_path):
             assert r["DCPreESR"] == pytest.approx(float(DCPreESR()(y1[:, :, 1024:], td[:, :, 1024:])), rel=1e-6)
             assert np.isfinite(r["ESR"]) and r["ESR"] > 0.0 and np.isfinite(r["DCPreESR"])
     assert res[-1]["input_name"].endswith("_[1000:4000].wav")
+
+
+def test_read_trajectory_dict_and_plain_files(tmp_path):
+    t = np.linspace(0.004, 0.006, 1000)
+    pd_, pp = str(tmp_path / "trajectory_1_.npy"), str(tmp_path / "plain.npy")
+    np.save(pd_, {"delay_trajectory": t, "input_peaks": np.arange(3), "output_peaks": np.arange(3)})   # the dataset's format
+    np.save(pp, t.astype(np.float32))
+    assert np.array_equal(driver.read_trajectory(pd_), t)
+    assert np.array_equal(driver.read_trajectory(pd_, 100, 250), t[100:350])
+    assert np.allclose(driver.read_trajectory(pp, 990, 500), t[990:], rtol=1e-6)
+    res = [{"ESR": 1.0, "DCPreESR": 4.0}, {"ESR": 3.0, "DCPreESR": 0.0}]
+    assert driver.mean_losses(res) == {"ESR": 2.0, "DCPreESR": 2.0}
+    assert driver.mean_losses([{"frames": 3}]) == {}
+
+
+def _delay_examples(tmp_path, lens, fs=44100, seed=2):
+    rng = np.random.default_rng(seed)
+    x = signals.stream_batch(len(lens), max(lens), dur=1.0)
+    d = signals.delay_trajectory(len(lens), max(lens)) / fs                 # the dataset stores SECONDS
+    examples = []
+    for i, n in enumerate(lens):
+        pi, pt, pj = (str(tmp_path / f"input_{i}_.wav"), str(tmp_path / f"target_{i}_.wav"),
+                      str(tmp_path / f"trajectory_{i}_.npy"))
+        driver.write_wav(pi, np.stack([x[i, :n], (np.arange(n) % 441 == 0).astype(np.float32)]), fs)
+        driver.write_wav(pt, 0.8 * x[i, :n] + 0.01 * rng.standard_normal(n).astype(np.float32), fs)
+        np.save(pj, {"delay_trajectory": d[i, :n].astype(np.float64)})
+        examples.append({"input_file": pi, "target_file": pt, "trajectory_file": pj})
+    examples.append(dict(examples[1], offset=500, length=2500))             # a dataset-style segment of file 1
+    return examples
+
+
+def _traj_samples(ex, dev):
+    a, fs = driver.read_wav(ex["input_file"], ex.get("offset", 0), ex.get("length", -1))
+    t = driver.read_trajectory(ex["trajectory_file"], ex.get("offset", 0), ex.get("length", -1))
+    return a, fs, (torch.from_numpy(t.astype(np.float32)) * float(fs)).to(dev).reshape(1, 1, -1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["fp32", "f16"])
+def test_batched_evaluator_diffdel_equals_one_file_at_a_time(tmp_path, mode):
+    from ntm_b200 import DiffDelRNN
+    dev = "cuda:0"
+    m = DiffDelRNN(1, 64, 1, False, max_delay=signals.DELAY_MAX).to(dev)
+    m.load_state_dict(load_ckpt("cfg3"))
+    m.mode = mode
+    examples = _delay_examples(tmp_path, [5000, 7321, 2048, 6000, 4097])
+    res = driver.BatchedEvaluator(m, max_streams=4).run(examples, out_dir=str(tmp_path / "pred"), init_len=512,
+                                                        write_pre_d=True)
+    with torch.inference_mode():
+        for ex, r in zip(examples, res):
+            a, fs, d = _traj_samples(ex, dev)
+            t, _ = driver.read_wav(ex["target_file"], ex.get("offset", 0), ex.get("length", -1))
+            y1, p1 = m.predict(torch.from_numpy(a[0]).to(dev).reshape(1, 1, -1), d)     # the reference's per-file call
+            assert np.array_equal(driver.read_wav(r["output_file"])[0][0], y1.cpu().numpy().reshape(-1))
+            assert np.array_equal(driver.read_wav(r["pre_d_file"])[0][0], p1.cpu().numpy().reshape(-1))
+            td = torch.from_numpy(t[0]).to(dev).reshape(1, 1, -1)
+            assert r["ESR"] == pytest.approx(float(ESRLoss()(y1[:, :, 512:], td[:, :, 512:])), rel=1e-6)
+            assert r["DCPreESR"] == pytest.approx(float(DCPreESR()(y1[:, :, 512:], td[:, :, 512:])), rel=1e-6)
+    means = driver.mean_losses(res)
+    assert means["ESR"] == pytest.approx(np.mean([r["ESR"] for r in res]))
+
+
+@pytest.mark.gpu
+def test_batched_evaluator_add_delay_equals_reference_style_chunk_loop(tmp_path):
+    """GRU + stand-alone delay line (ADD_DELAY): one batched call == per file, 4096-sample chunks with a carried buffer
+    (apply_delay, code/test-model.py:259-290)."""
+    from ntm_b200 import TimeVaryingDelayLine
+    dev = "cuda:0"
+    m = RNN(1, 64, 1, False).to(dev)
+    m.load_state_dict(load_ckpt("cfg2"))
+    examples = _delay_examples(tmp_path, [9000, 4096, 12345, 100])
+    delay = TimeVaryingDelayLine(max_delay=signals.DELAY_MAX)
+    res = driver.BatchedEvaluator(m, max_streams=3, delay=delay).run(examples, out_dir=str(tmp_path / "pred"),
+                                                                     init_len=64)
+    ref_delay = TimeVaryingDelayLine(max_delay=signals.DELAY_MAX)
+    with torch.inference_mode():
+        for ex, r in zip(examples, res):
+            a, fs, d = _traj_samples(ex, dev)
+            y = m.predict(torch.from_numpy(a[0]).to(dev).reshape(1, 1, -1))
+            ref_delay.init_buffer(1)
+            out = torch.cat([ref_delay(y[:, :, s:s + 4096], d[:, :, s:s + 4096]) for s in range(0, y.shape[-1], 4096)], -1)
+            assert np.array_equal(driver.read_wav(r["output_file"])[0][0], out.cpu().numpy().reshape(-1))
+            t, _ = driver.read_wav(ex["target_file"], ex.get("offset", 0), ex.get("length", -1))
+            td = torch.from_numpy(t[0]).to(dev).reshape(1, 1, -1)
+            assert r["ESR"] == pytest.approx(float(ESRLoss()(out[:, :, 64:], td[:, :, 64:])), rel=1e-6)
+    with pytest.raises(ValueError):
+        driver.BatchedEvaluator(__import__("ntm_b200").DiffDelRNN(1, 64, 1, False, max_delay=8), delay=delay)

@@ -125,3 +125,33 @@ def test_dcpre_esr_oracle_vs_reference_golden():
         assert abs(pl - float(g[f"esr_{case}"])) <= 2e-5 * abs(float(g[f"esr_{case}"])) + 1e-9, case
         n = g[f"o_{case}"].size
         assert abs(dc - (num / n) / (den / n + 1e-5)) < 1e-12
+
+
+def _best12():
+    g = load_golden("golden_best12")
+    for i in range(int(g["n"])):
+        pre = f"w{i}_"
+        sd = {k[len(pre):]: torch.from_numpy(g[k]) for k in g.files if k.startswith(pre)}
+        yield i, str(g[f"kind{i}"]), sd, g
+
+
+def test_c_oracle_on_all_12_shipped_best_checkpoints():
+    """Every `weights/*_BEST/best.pth` (6 GRU, 6 DiffDelGRU): warm-start known answer and predict() on two signals vs the
+    reference's own outputs (oracle/make_golden_best.py).  Tolerance: float32 round-off, or 4x the reference's own
+    fp32-vs-fp64 floor where the checkpoint is chaotic on the signal."""
+    n = 0
+    for i, kind, sd, g in _best12():
+        w = c_oracle.GruWeights.from_state_dict(sd)
+        assert (w.b_out is None) == (kind == "DiffDelGRU")
+        _, h1 = c_oracle.gru_forward(w, np.zeros((1, 1024), np.float32))
+        assert np.max(np.abs(h1.reshape(-1) - g[f"h_warm{i}"])) < 5e-6, i
+        for sig in g["signals"]:
+            x, tol = g[f"x_{sig}"].reshape(1, -1), max(5e-6, 4.0 * float(g[f"floor{i}_{sig}"]))
+            if kind == "GRU":
+                y, _ = c_oracle.rnn_predict(w, x)
+            else:
+                y, pre, _, _ = c_oracle.diffdel_predict(w, x, g[f"d_{sig}"].reshape(1, -1), int(g["max_delay"]))
+                assert np.max(np.abs(pre.reshape(-1) - g[f"pre{i}_{sig}"])) < tol, (i, sig)
+            assert np.max(np.abs(y.reshape(-1) - g[f"y{i}_{sig}"])) < tol, (i, sig)
+        n += 1
+    assert n == 12

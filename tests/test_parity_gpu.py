@@ -339,3 +339,59 @@ def test_cfg2_width_properties():
         assert float((y[pick].cpu() - yr).abs().max()) <= TOL
         assert torch.isfinite(y).all()
     assert lib.query(lib.Q_KERNEL_LAUNCHES) > 0
+
+
+# ------------------------------------------------------------------- all 12 shipped `_BEST` checkpoints
+def _best12():
+    g = load_golden("golden_best12")
+    for i in range(int(g["n"])):
+        pre = f"w{i}_"
+        yield i, str(g[f"kind{i}"]), {k[len(pre):]: torch.from_numpy(g[k]) for k in g.files if k.startswith(pre)}, g
+
+
+@pytest.mark.parametrize("mode", ["fp32", "f16"])
+def test_all_12_shipped_best_checkpoints_vs_reference(mode):
+    """`load_state_dict(strict=True)` of every weights/*_BEST/best.pth into the drop-in classes, warm-start known answer,
+    and predict() on two signals against the REFERENCE's outputs (oracle/make_golden_best.py), packed as a batch of 3
+    identical streams (B > 1 == B separate reference calls).  fp32: max-abs <= 1e-5 (widened by twice the reference's own
+    fp32-vs-fp64 floor where that is above 3e-6); f16 operands: ESR <= 1e-4 on stable cases."""
+    n = 0
+    for i, kind, sd, g in _best12():
+        if kind == "GRU":
+            m = RNN(input_size=1, hidden_size=64, output_size=1, skip=False).to(DEV)
+        else:
+            m = DiffDelRNN(input_size=1, hidden_size=64, output_size=1, skip=False, max_delay=int(g["max_delay"])).to(DEV)
+        res = m.load_state_dict(sd, strict=True)
+        assert not res.missing_keys and not res.unexpected_keys
+        assert "diffdel.buffer" not in m.state_dict()
+        m.mode = mode
+        with torch.inference_mode():
+            if kind == "GRU":
+                m.initialize_hidden()
+            else:
+                m.initialize_hidden(1, int(g["max_delay"]))
+            m.warm_start()
+            hw = m.hidden.cpu().numpy().reshape(-1)
+            assert np.max(np.abs(hw - g[f"h_warm{i}"])) < (5e-6 if mode == "fp32" else 2e-3), (i, mode)
+            for sig in g["signals"]:
+                floor = float(g[f"floor{i}_{sig}"])
+                x = dev(g[f"x_{sig}"]).reshape(1, 1, -1).expand(3, 1, -1).contiguous()
+                if kind == "GRU":
+                    y = m.predict(x).cpu().numpy()
+                    outs = [(y, g[f"y{i}_{sig}"])]
+                else:
+                    d = dev(g[f"d_{sig}"]).reshape(1, 1, -1).expand(3, 1, -1).contiguous()
+                    y, pre = m.predict(x, d)
+                    outs = [(y.cpu().numpy(), g[f"y{i}_{sig}"]), (pre.cpu().numpy(), g[f"pre{i}_{sig}"])]
+                for got, want in outs:
+                    assert np.array_equal(got[0], got[1]) and np.array_equal(got[0], got[2])
+                    if mode == "fp32":
+                        err = float(np.max(np.abs(got[0, 0] - want)))
+                        assert err <= tol_for(floor), (i, kind, sig, err, floor)
+                    elif floor < 3e-6:
+                        esr = c_oracle.esr(got[0, 0], want)
+                        assert esr <= 1e-4, (i, kind, sig, esr)
+                    else:
+                        assert np.all(np.isfinite(got))
+        n += 1
+    assert n == 12
