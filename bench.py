@@ -453,7 +453,41 @@ def aux_measurements(ntm_b200, signals, dev, mode):
         gbs = 8.0 * Bl * Tl / (best * 1e-3) / 1e9
         losses[name] = {"samples_per_s": Bl * Tl / (best * 1e-3), "hbm_gbs": gbs, "frac_of_measured_hbm_peak": gbs / hbm_peak}
     out["loss_pass_1024x30s"] = losses
+    del tl, ol
+    out["existing_gpu_path_cudnn"] = cudnn_bar(dev)
     return out
+
+
+def cudnn_bar(dev):
+    """The "existing GPU kernel" bar of SURVEY.md section 8d: what `model.RNN(...).cuda()` runs today -- torch.nn.GRU (cuDNN)
+    + nn.Linear in fp32, driven like code/model.py:218-246 (2048-sample segments with carried hidden state) -- on the cfg 2
+    checkpoint, 1024 streams x 1 s, same B200, CUDA events.  Library code timed beside the product; it is not the product."""
+    sd = load_sd("cfg2")
+    B, T, SEG = 1024, FS, 2048
+    gru = torch.nn.GRU(1, 64, batch_first=True).to(dev)
+    head = torch.nn.Linear(64, 1).to(dev)
+    gru.load_state_dict({k[4:]: v for k, v in sd.items() if k.startswith("GRU.")})
+    head.load_state_dict({k[7:]: v for k, v in sd.items() if k.startswith("output.")})
+    x = 0.1 * torch.randn(B, T, 1, device=dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def run():
+        h, ys = None, []
+        for s0 in range(0, T, SEG):
+            hs, h = gru(x[:, s0:s0 + SEG], h)
+            ys.append(head(hs))
+        return ys
+
+    with torch.inference_mode():
+        run()
+        torch.cuda.synchronize(dev)
+        best = 1e9
+        for _ in range(2):
+            e0.record(); run(); e1.record(); torch.cuda.synchronize(dev)
+            best = min(best, e0.elapsed_time(e1))
+    return {"samples_per_s": B * T / (best * 1e-3), "ns_per_timestep": best * 1e6 / T,
+            "sample": f"{B} streams x {T} samples in {SEG}-sample segments, torch.nn.GRU (cuDNN {torch.backends.cudnn.version()}) "
+                      "+ nn.Linear, fp32"}
 
 
 if __name__ == "__main__":

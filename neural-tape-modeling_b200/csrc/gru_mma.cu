@@ -95,7 +95,8 @@ struct MmaCfg {
 // processes one block of a.T samples per mailbox hand-shake (a.rt, mapped host memory; a.x / a.y point into it), so a block
 // costs two PCIe round trips instead of a kernel launch, a prologue and a stream synchronisation.
 template <int FMT, int NT, bool HALF, bool RT = false>
-__global__ void __launch_bounds__(128, FMT == FMT_TF32 ? 2 : 4) gru_mma_kernel(const GruArgs a)
+// (HALF is only dispatched up to two CTAs per SM: the full register file removes its spills, 197 vs 204 ns/step)
+__global__ void __launch_bounds__(128, (FMT == FMT_TF32 || HALF) ? 2 : 4) gru_mma_kernel(const GruArgs a)
 {
     static_assert(!HALF || NT == 1, "HALF needs a single n8 tile");
     static_assert(!RT || HALF, "the real-time server uses the 4-streams-per-CTA form");
@@ -328,6 +329,19 @@ __global__ void __launch_bounds__(128, FMT == FMT_TF32 ? 2 : 4) gru_mma_kernel(c
                 load_bfrag(hcur, nt, breg[nt]);
 #pragma unroll
                 for (int tile = 0; tile < 3; ++tile) acc[nt][tile][0] = acc[nt][tile][1] = acc[nt][tile][2] = acc[nt][tile][3] = 0.0f;
+                if (!HALF) {
+                    // throughput form: input projection and biases enter through the accumulators (fewer FP32 instructions
+                    // after the MMAs: 976 vs 1027 ns/step at 8192 streams; the 4-stream latency form measured slower with it)
+                    const float2 xi = *reinterpret_cast<const float2*>(xcur + tt * S + nt * 8 + 2 * tig);
+#pragma unroll
+                    for (int u = 0; u < 2; ++u)
+#pragma unroll
+                        for (int e = 0; e < NE; ++e) {
+                            acc[nt][0][2 * u + e] = fmaf(uc[u].cr_w, e ? xi.y : xi.x, uc[u].cr_b);
+                            acc[nt][1][2 * u + e] = fmaf(uc[u].cz_w, e ? xi.y : xi.x, uc[u].cz_b);
+                            acc[nt][2][2 * u + e] = uc[u].ch_b;
+                        }
+                }
             }
             // critical path first: r -> n -> h' is the dependent chain of the step, z only enters the final blend.  The r and
             // n tiles alternate (two dependent accumulator chains keep the pipe busy), the z tile follows and overlaps r's
@@ -363,11 +377,19 @@ __global__ void __launch_bounds__(128, FMT == FMT_TF32 ? 2 : 4) gru_mma_kernel(c
 #pragma unroll
                 for (int u = 0; u < 2; ++u)
 #pragma unroll
-                    for (int e = 0; e < NE; ++e)
+                    for (int e = 0; e < NE; ++e) {
                         // r has its own reciprocal at every width: sharing 1/(d_r d_z) (4.5 instead of 5.5 MUFU per pair)
                         // measured slower even in the throughput regime (1052 vs 1030 ns/step at 8192 streams)
-                        gates_rz_dn_fast_r(uc[u], acc[nt][0][2 * u + e], acc[nt][1][2 * u + e], acc[nt][2][2 * u + e],
-                                           e ? xv.y : xv.x, z[u][e], dn[u][e]);
+                        const float xx = e ? xv.y : xv.x;
+                        if (HALF) {
+                            gates_rz_dn_fast_r(uc[u], acc[nt][0][2 * u + e], acc[nt][1][2 * u + e], acc[nt][2][2 * u + e], xx,
+                                               z[u][e], dn[u][e]);
+                        } else {                   // accumulators already hold W_i x + b (r, z) and b_hn (n)
+                            const float r = rcp_approx(1.0f + ex2_approx(acc[nt][0][2 * u + e]));
+                            dn[u][e] = 1.0f + ex2_approx(fminf(fmaf(r, acc[nt][2][2 * u + e], fmaf(uc[u].cn_w, xx, uc[u].cn_b)), EX2_CLAMP));
+                            z[u][e] = rcp_approx(1.0f + ex2_approx(acc[nt][1][2 * u + e]));
+                        }
+                    }
 #pragma unroll
                 for (int e = 0; e < NE; ++e) {
                     if (HALF) {                    // MUFU slots to spare: own n-gate reciprocals, shorter dependent chain

@@ -372,7 +372,7 @@ def test_all_12_shipped_best_checkpoints_vs_reference(mode):
                 m.initialize_hidden(1, int(g["max_delay"]))
             m.warm_start()
             hw = m.hidden.cpu().numpy().reshape(-1)
-            assert np.max(np.abs(hw - g[f"h_warm{i}"])) < (5e-6 if mode == "fp32" else 2e-3), (i, mode)
+            assert np.max(np.abs(hw - g[f"h_warm{i}"])) < (5e-6 if mode == "fp32" else 5e-3), (i, mode)
             for sig in g["signals"]:
                 floor = float(g[f"floor{i}_{sig}"])
                 x = dev(g[f"x_{sig}"]).reshape(1, 1, -1).expand(3, 1, -1).contiguous()
