@@ -275,9 +275,9 @@ def main():
             "bound": "tensor", "achieved": achieved_tflops, "peak": tensor_peak, "unit": "TFLOP/s",
             "frac": achieved_tflops / tensor_peak,
             # dram__bytes_read+write of this kernel from one `ncu --set full` capture (profiles/r01_mma_b1024_ncu.txt:
-            # 20.0 MB for 1024 x 4800 samples = the x reads; the y writes of that capture stayed in the 126 MB L2),
-            # scaled to this launch's sample count
-            "traffic": round(20.0e6 / (1024 * 4800) * B * T), "algorithmic_bytes": BYTES_PER_SAMPLE * B * T,
+            # 395.3 MB read + 355.4 MB written for 1024 x 96 000 samples = 7.64 B per sample against 8 algorithmic -- the
+            # last ~10 % of the y writes were still in the 126 MB L2 when the kernel ended), scaled to this launch
+            "traffic": round(750.7e6 / (1024 * 96000) * B * T), "algorithmic_bytes": BYTES_PER_SAMPLE * B * T,
             "peak_source": peak_src,
             "kernel_ms": kern_ms, "kernel": kernel_name,
             "regime": "latency-bound recurrence: 1024 streams = 7 per SM, one dependent GRU step at a time (DESIGN.md section 4)",

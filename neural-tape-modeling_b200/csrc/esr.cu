@@ -24,7 +24,8 @@ namespace {
 
 constexpr int ESR_TAPS = 2000;
 constexpr int ESR_WARM = 2048;           // >= ESR_TAPS - 1, multiple of the 128-sample tile
-constexpr int ESR_PF = 4;                // tiles of global loads in flight per warp
+constexpr int ESR_SPL = 8;               // samples per lane and scan (multiple of 4): the 5 shuffle steps are paid per 32 x SPL samples
+constexpr int ESR_PF = 2;                // tiles of global loads in flight per warp
 constexpr int ESR_RING = 2048;           // on-chip window of past samples: power of two, >= ESR_TAPS
 // DCPreESR: one warp per CTA -- every loop bound then derives from blockIdx and the compiler keeps the control flow on the
 // uniform datapath (with 4 warps per CTA it doubled the shuffles, wrapped them in WARPSYNC pairs and emitted 5x the IMADs).
@@ -68,15 +69,15 @@ __global__ void __launch_bounds__(32 * esr_warps(DCPRE)) esr_kernel(const float*
             den = fma(tv, tv, den);
         }
     } else {
-        const double R2 = R * R, D = R2 * R2;                    // decay over one lane's 4 samples
+        constexpr int SPL = ESR_SPL, TILE = 32 * SPL;             // samples per lane and per warp iteration
+        double D = 1.0;                                           // decay over one lane's samples
+#pragma unroll
+        for (int i = 0; i < SPL; ++i) D *= R;
         const double Dk[5] = {D, D * D, (D * D) * (D * D), ((D * D) * (D * D)) * ((D * D) * (D * D)),
                               (((D * D) * (D * D)) * ((D * D) * (D * D))) * (((D * D) * (D * D)) * ((D * D) * (D * D)))};
-        const double D32 = Dk[4] * Dk[4];
+        const double D32 = Dk[4] * Dk[4];                         // decay over one tile
         double Dl = 1.0;                                          // D^lane
         for (int i = 0; i < lane; ++i) Dl *= D;
-        double Dm[5];                                             // scan multipliers, zero where the partner lane is out of range
-#pragma unroll
-        for (int k = 0; k < 5; ++k) Dm[k] = lane >= (1 << k) ? Dk[k] : 0.0;
         const double g = R - 1.0;
         double se_tile = 0.0, st_tile = 0.0;                      // S of e / of t at the sample before the tile
         const long long n0 = c0 >= ESR_WARM ? c0 - ESR_WARM : 0;
@@ -91,74 +92,88 @@ __global__ void __launch_bounds__(32 * esr_warps(DCPRE)) esr_kernel(const float*
 #pragma unroll
         for (int i = 0; i < ESR_RING / 128; ++i) *reinterpret_cast<uint4*>(ring + 128 * i + 4 * lane) = make_uint4(0u, 0u, 0u, 0u);
         __syncwarp();
-        // rows 16-byte aligned (tiles start at multiples of 128 samples): vector loads in the interior tiles
+        // rows 16-byte aligned (tiles start at multiples of TILE samples): vector loads in the interior tiles
         const bool aligned = (((unsigned long long)o | (unsigned long long)t) & 15ull) == 0;
         // raw samples of one tile (zero outside [0, T))
-        auto fetch = [&](long long nb, float (&tv)[4], float (&ov)[4]) {
-            if (aligned && nb + 128 <= T) {                       // interior tile (warp-uniform): 16-byte loads, no checks
-                const float4 a = __ldg(reinterpret_cast<const float4*>(t + nb + 4 * lane));
-                const float4 b = __ldg(reinterpret_cast<const float4*>(o + nb + 4 * lane));
-                tv[0] = a.x; tv[1] = a.y; tv[2] = a.z; tv[3] = a.w;
-                ov[0] = b.x; ov[1] = b.y; ov[2] = b.z; ov[3] = b.w;
+        auto fetch = [&](long long nb, float (&tv)[SPL], float (&ov)[SPL]) {
+            if (aligned && nb + TILE <= T) {                      // interior tile (warp-uniform): 16-byte loads, no checks
+#pragma unroll
+                for (int q = 0; q < SPL / 4; ++q) {
+                    const float4 a = __ldg(reinterpret_cast<const float4*>(t + nb + SPL * lane) + q);
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(o + nb + SPL * lane) + q);
+                    tv[4 * q] = a.x; tv[4 * q + 1] = a.y; tv[4 * q + 2] = a.z; tv[4 * q + 3] = a.w;
+                    ov[4 * q] = b.x; ov[4 * q + 1] = b.y; ov[4 * q + 2] = b.z; ov[4 * q + 3] = b.w;
+                }
                 return;
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const long long nn = nb + 4 * lane + j;
+            for (int j = 0; j < SPL; ++j) {
+                const long long nn = nb + SPL * lane + j;
                 const bool in = nn < T;
                 tv[j] = in ? __ldg(t + nn) : 0.0f;
                 ov[j] = in ? __ldg(o + nn) : 0.0f;
             }
         };
-        // ESR_PF tiles of loads in flight per warp (4 KB): with ~13 resident warps per SM (the rings), one tile ahead left the
+        // ESR_PF tiles of loads in flight per warp: with the rings limiting the resident warps, one tile ahead left the
         // pass bound by DRAM latency, not bandwidth
-        float pft[ESR_PF][4], pfo[ESR_PF][4];
+        float pft[ESR_PF][SPL], pfo[ESR_PF][SPL];
 #pragma unroll
         for (int u = 0; u < ESR_PF; ++u)
-            if (n0 + 128 * u < c1) fetch(n0 + 128 * u, pft[u], pfo[u]);
-        // Precision split: everything per sample is fp32 -- a tile-local scan from zero state only ever holds sums of <= 128
+            if (n0 + TILE * u < c1) fetch(n0 + TILE * u, pft[u], pfo[u]);
+        // Precision split: everything per sample is fp32 -- a tile-local scan from zero state only ever holds sums of <= TILE
         // decayed samples, and f = x + g S with g = -0.005 damps S's rounding (6e-8 |S|, |S| <~ 200 |x|) to 6e-8 |x|, the
-        // quantisation of the float32 audio itself -- while the carries across tiles (se_tile, st_tile: ~16 tiles of history)
-        // and the two sums stay in double.  Per tile and signal: 3 fp64 instructions + 3 conversions instead of ~30 + 8.
+        // quantisation of the float32 audio itself -- while the carries across tiles (se_tile, st_tile) and the two sums
+        // stay in double.  Per tile and signal: 3 fp64 instructions + 3 conversions instead of ~30 + 8.
         const float Rf = (float)R, gf = (float)g, Rwf = (float)Rw;
-        float Dmf[5];
+        float Dmf[5];                                             // scan multipliers, zero where the partner lane is out of range
 #pragma unroll
-        for (int k = 0; k < 5; ++k) Dmf[k] = (float)Dm[k];
-        for (long long nb0 = n0; nb0 < c1; nb0 += 128 * ESR_PF) {
+        for (int k = 0; k < 5; ++k) Dmf[k] = lane >= (1 << k) ? (float)Dk[k] : 0.0f;
+        for (long long nb0 = n0; nb0 < c1; nb0 += TILE * ESR_PF) {
 #pragma unroll
           for (int u = 0; u < ESR_PF; ++u) {
-            const long long nb = nb0 + 128 * u;
+            const long long nb = nb0 + TILE * u;
             if (nb >= c1) break;                                  // (warp-uniform)
-            const long long n = nb + 4 * lane;
-            float xe[4], xt[4], ue[4], ut[4];
+            const long long n = nb + SPL * lane;
+            float xe[SPL], xt[SPL], ue[SPL], ut[SPL];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < SPL; ++j) {
                 xt[j] = pft[u][j];
                 xe[j] = pft[u][j] - pfo[u][j];
             }
             // refill this buffer with the tile ESR_PF ahead
-            if (nb + 128 * ESR_PF < c1) fetch(nb + 128 * ESR_PF, pft[u], pfo[u]);
+            if (nb + TILE * ESR_PF < c1) fetch(nb + TILE * ESR_PF, pft[u], pfo[u]);
             {
-                // samples n - 1999 .. n - 1996 = elements 1..3 of the aligned ring vector at n - 2000 and the first element
-                // of the next lane's vector (lane 31: one scalar read); read the window BEFORE this tile overwrites its slot
-                const int rp = (int)((nb + 4 * lane + (ESR_RING - ESR_TAPS)) & (ESR_RING - 1));
-                const uint4 c = *reinterpret_cast<const uint4*>(ring + rp);
-                uint32_t cn = __shfl_down_sync(0xffffffffu, c.x, 1);
-                if (lane == 31) cn = ring[(rp + 4) & (ESR_RING - 1)];
-                __syncwarp();
-                const int wp = (int)((nb + 4 * lane) & (ESR_RING - 1));
-                *reinterpret_cast<uint4*>(ring + wp) = make_uint4(bf16_pair(xt[0], xe[0]), bf16_pair(xt[1], xe[1]),
-                                                                  bf16_pair(xt[2], xe[2]), bf16_pair(xt[3], xe[3]));
-                const uint32_t dl[4] = {c.y, c.z, c.w, cn};
+                // samples n - 1999 .. n - 2000 + SPL = elements 1 .. SPL - 1 of the aligned ring vectors at n - 2000 and the
+                // first element of the next lane's (lane 31: one scalar read); read BEFORE this tile overwrites its slots
+                const int rp = (int)((nb + SPL * lane + (ESR_RING - ESR_TAPS)) & (ESR_RING - 1));
+                uint32_t dl[SPL + 1];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    ut[j] = fmaf(-Rwf, __uint_as_float(dl[j] << 16), xt[j]);
-                    ue[j] = fmaf(-Rwf, __uint_as_float(dl[j] & 0xffff0000u), xe[j]);
+                for (int q = 0; q < SPL / 4; ++q) {
+                    const uint4 c = *reinterpret_cast<const uint4*>(ring + ((rp + 4 * q) & (ESR_RING - 1)));
+                    dl[4 * q] = c.x; dl[4 * q + 1] = c.y; dl[4 * q + 2] = c.z; dl[4 * q + 3] = c.w;
+                }
+                dl[SPL] = __shfl_down_sync(0xffffffffu, dl[0], 1);
+                if (lane == 31) dl[SPL] = ring[(rp + SPL) & (ESR_RING - 1)];
+                __syncwarp();
+                const int wp = (int)((nb + SPL * lane) & (ESR_RING - 1));
+#pragma unroll
+                for (int q = 0; q < SPL / 4; ++q)
+                    *reinterpret_cast<uint4*>(ring + wp + 4 * q) =
+                        make_uint4(bf16_pair(xt[4 * q], xe[4 * q]), bf16_pair(xt[4 * q + 1], xe[4 * q + 1]),
+                                   bf16_pair(xt[4 * q + 2], xe[4 * q + 2]), bf16_pair(xt[4 * q + 3], xe[4 * q + 3]));
+#pragma unroll
+                for (int j = 0; j < SPL; ++j) {
+                    ut[j] = fmaf(-Rwf, __uint_as_float(dl[j + 1] << 16), xt[j]);
+                    ue[j] = fmaf(-Rwf, __uint_as_float(dl[j + 1] & 0xffff0000u), xe[j]);
                 }
             }
             // lane aggregates from zero state, inclusive decayed scan over the lanes
-            float ae = fmaf(fmaf(fmaf(ue[0], Rf, ue[1]), Rf, ue[2]), Rf, ue[3]);
-            float at = fmaf(fmaf(fmaf(ut[0], Rf, ut[1]), Rf, ut[2]), Rf, ut[3]);
+            float ae = ue[0], at = ut[0];
+#pragma unroll
+            for (int j = 1; j < SPL; ++j) {
+                ae = fmaf(ae, Rf, ue[j]);
+                at = fmaf(at, Rf, ut[j]);
+            }
 #pragma unroll
             for (int k = 0; k < 5; ++k) {
                 const float pe = __shfl_up_sync(0xffffffffu, ae, 1 << k), pt = __shfl_up_sync(0xffffffffu, at, 1 << k);
@@ -170,10 +185,10 @@ __global__ void __launch_bounds__(32 * esr_warps(DCPRE)) esr_kernel(const float*
             se += (float)(Dl * se_tile);                          // S at the sample before this lane's first
             st += (float)(Dl * st_tile);
             if (nb >= c0) {                                       // (warm-up tiles only feed the carry below)
-                const bool full = nb + 128 <= c1;                 // tile entirely inside the chunk (warp-uniform)
+                const bool full = nb + TILE <= c1;                // tile entirely inside the chunk (warp-uniform)
                 float pn = 0.0f, pd = 0.0f;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < SPL; ++j) {
                     const float fe = fmaf(gf, se, xe[j]), ft = fmaf(gf, st, xt[j]);
                     if (full || n + j < c1) { pn = fmaf(fe, fe, pn); pd = fmaf(ft, ft, pd); }
                     se = fmaf(Rf, se, ue[j]);
