@@ -453,7 +453,21 @@ def aux_measurements(ntm_b200, signals, dev, mode):
         gbs = 8.0 * Bl * Tl / (best * 1e-3) / 1e9
         losses[name] = {"samples_per_s": Bl * Tl / (best * 1e-3), "hbm_gbs": gbs, "frac_of_measured_hbm_peak": gbs / hbm_peak}
     out["loss_pass_1024x30s"] = losses
-    del tl, ol
+    # stand-alone delay line (apply_delay): 12 algorithmic bytes per sample (x, d read; y written)
+    dline = ntm_b200.TimeVaryingDelayLine(max_delay=signals.DELAY_MAX)
+    dline.check_delay = False
+    dtr = signals.delay_trajectory_device(Bl, Tl, dev).reshape(Bl, 1, Tl)
+    dline.init_buffer(Bl)
+    dline(ol, dtr)
+    best = 1e9
+    for _ in range(3):
+        dline.init_buffer(Bl)
+        e0.record(); dline(ol, dtr); e1.record(); torch.cuda.synchronize(dev)
+        best = min(best, e0.elapsed_time(e1))
+    gbs = 12.0 * Bl * Tl / (best * 1e-3) / 1e9
+    out["delay_pass_1024x30s"] = {"samples_per_s": Bl * Tl / (best * 1e-3), "hbm_gbs": gbs,
+                                  "frac_of_measured_hbm_peak": gbs / hbm_peak}
+    del tl, ol, dtr
     out["existing_gpu_path_cudnn"] = cudnn_bar(dev)
     return out
 
