@@ -175,7 +175,18 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+        # keep stdout to the ONE JSON line: NCCL prints its version banner (and NCCL_DEBUG output) to stdout when the
+        # communicator comes up, i.e. at the first collective -- do that here with fd 1 pointed at stderr
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
 
     B, T = args.streams, int(round(args.seconds * FS))
     model = ntm_b200.RNN(input_size=1, hidden_size=64, output_size=1, skip=False).to(dev)
