@@ -78,7 +78,7 @@ __device__ __forceinline__ void store_state2(uint8_t* row, int unit, float v0, f
 template <int FMT, int NT>
 struct MmaCfg {
     static constexpr int S = 8 * NT;                 // streams per CTA
-    static constexpr int CH = 32;                    // steps per staged chunk
+    static constexpr int CH = 128;                   // steps per staged chunk (measured at 1024 streams: 32 -> 232.7 ns/step, 64 -> 238, 128 -> 221.7, 256 -> 220.1)
     static constexpr int YP_LD = S + 2;              // even: float2 stores of the head partials
     static constexpr int HB_BYTES = S * Frag<FMT>::ROW_BYTES;
     static constexpr int OFF_HB = 0;                               // [2][S][ROW_BYTES]
@@ -347,6 +347,10 @@ __global__ void __launch_bounds__(128, (FMT == FMT_TF32 || HALF) ? 2 : 4) gru_mm
             // n tiles alternate (two dependent accumulator chains keep the pipe busy), the z tile follows and overlaps r's
             // gate math.  (Measured 233.7 vs 239.1 ns/step at 1024 streams against the ks-outer order over tiles that mixed
             // r and z rows; splitting z into two half-K chains gained nothing; bit-identical results.)
+#if defined(NTM_X3)
+            if (false)
+#endif
+            {
 #pragma unroll
             for (int ks = 0; ks < NK; ++ks)
 #pragma unroll
@@ -359,6 +363,7 @@ __global__ void __launch_bounds__(128, (FMT == FMT_TF32 || HALF) ? 2 : 4) gru_mm
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt)
                     mma_sync<FMT>(acc[nt][1], areg[1][ks], breg[nt][2 * ks], breg[nt][2 * ks + 1]);
+            }
 
             // ---- head of the PREVIOUS step from the same B fragments (see `ahead`) -------------------------------
 #pragma unroll
@@ -393,8 +398,13 @@ __global__ void __launch_bounds__(128, (FMT == FMT_TF32 || HALF) ? 2 : 4) gru_mm
 #pragma unroll
                 for (int e = 0; e < NE; ++e) {
                     if (HALF) {                    // MUFU slots to spare: own n-gate reciprocals, shorter dependent chain
+#if defined(NTM_X2)                                // ablation (wrong results): no gate math, keep the data flow
+                        hn[0][e] = 0.001f * (acc[nt][0][e] + acc[nt][1][e] + acc[nt][2][e]) + 0.5f * hst[nt][0][e];
+                        hn[1][e] = 0.001f * (acc[nt][0][2 + e] + acc[nt][1][2 + e] + acc[nt][2][2 + e]) + 0.5f * hst[nt][1][e];
+#else
                         hn[0][e] = gates_blend1(z[0][e], dn[0][e], hst[nt][0][e]);
                         hn[1][e] = gates_blend1(z[1][e], dn[1][e], hst[nt][1][e]);
+#endif
                     } else {                       // the two hidden units of one stream share the n-gate reciprocal
                         gates_blend2(z[0][e], dn[0][e], hst[nt][0][e], z[1][e], dn[1][e], hst[nt][1][e], hn[0][e], hn[1][e]);
                     }
