@@ -94,7 +94,9 @@ struct MmaCfg {
 // RT (HALF only): resident real-time server -- the CTA stays on its SM, keeps weights, state and staging on chip and
 // processes one block of a.T samples per mailbox hand-shake (a.rt, mapped host memory; a.x / a.y point into it), so a block
 // costs two PCIe round trips instead of a kernel launch, a prologue and a stream synchronisation.
-template <int FMT, int NT, bool HALF, bool RT = false>
+// DEFER (HALF only): the output head's accumulators are consumed one iteration later (see the head block); wins when a
+// warp has its SM sub-partition to itself (one CTA per SM: cfg 3, cfg 5, the real-time server), loses otherwise.
+template <int FMT, int NT, bool HALF, bool RT = false, bool DEFER = RT>
 // (HALF is only dispatched up to two CTAs per SM: the full register file removes its spills, 197 vs 204 ns/step)
 __global__ void __launch_bounds__(128, (FMT == FMT_TF32 || HALF) ? 2 : 4) gru_mma_kernel(const GruArgs a)
 {
@@ -319,6 +321,7 @@ __global__ void __launch_bounds__(128, (FMT == FMT_TF32 || HALF) ? 2 : 4) gru_mm
             if (use_ring) load_d(xb ^ 1, t0 + CH);
         }
 
+        float hpend[NT][4];
         for (int tt = 0; tt < n; ++tt) {
             const uint8_t* hcur = hb + cur * C::HB_BYTES;
             uint8_t* hnext = hb + (cur ^ 1) * C::HB_BYTES;
@@ -366,13 +369,26 @@ __global__ void __launch_bounds__(128, (FMT == FMT_TF32 || HALF) ? 2 : 4) gru_mm
             }
 
             // ---- head of the PREVIOUS step from the same B fragments (see `ahead`) -------------------------------
+            // DEFER: its accumulators are only consumed at the top of the NEXT iteration (hpend).  With the add + store in
+            // this iteration ptxas places them three instructions behind the head HMMA, in the middle of the r / n chains,
+            // and the in-order warp stalls there for the HMMA latency on every step: 189.9 -> 176.7 ns/step with one warp
+            // per SM sub-partition.  With two or more warps per sub-partition that stall is hidden by the other warps and
+            // the compact 12-HMMA burst of the deferred form collides on the tensor pipe instead (221 -> 232 ns/step at
+            // 1024 streams, 948 -> 1000 at 8192), so the immediate form stays there.
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) {
-                float ch[4];
-                head_mma(breg[nt], ch);
-                if (tt > 0 && gid == 0)
-                    *reinterpret_cast<float2*>(yp + (warp * CH + tt - 1) * C::YP_LD + nt * 8 + 2 * tig) =
-                        make_float2(ch[0] + ch[2], ch[1] + ch[3]);
+                if (DEFER) {
+                    if (tt > 1 && gid == 0)
+                        *reinterpret_cast<float2*>(yp + (warp * CH + tt - 2) * C::YP_LD + nt * 8 + 2 * tig) =
+                            make_float2(hpend[nt][0] + hpend[nt][2], hpend[nt][1] + hpend[nt][3]);
+                    head_mma(breg[nt], hpend[nt]);
+                } else {
+                    float ch[4];
+                    head_mma(breg[nt], ch);
+                    if (tt > 0 && gid == 0)
+                        *reinterpret_cast<float2*>(yp + (warp * CH + tt - 1) * C::YP_LD + nt * 8 + 2 * tig) =
+                            make_float2(ch[0] + ch[2], ch[1] + ch[3]);
+                }
             }
             // ---- gates, state blend, rounded state for the next step, head partials ------------------------------
 #pragma unroll
@@ -423,6 +439,9 @@ __global__ void __launch_bounds__(128, (FMT == FMT_TF32 || HALF) ? 2 : 4) gru_mm
         if (n > 0) {                           // head of the chunk's last step: one more MMA on the final state tile
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) {
+                if (DEFER && n > 1 && gid == 0) // (the pending head of the step before it)
+                    *reinterpret_cast<float2*>(yp + (warp * CH + n - 2) * C::YP_LD + nt * 8 + 2 * tig) =
+                        make_float2(hpend[nt][0] + hpend[nt][2], hpend[nt][1] + hpend[nt][3]);
                 uint32_t bfin[BW];
                 float ch[4];
                 load_bfrag(hb + cur * C::HB_BYTES, nt, bfin);
@@ -511,16 +530,24 @@ __global__ void __launch_bounds__(128, (FMT == FMT_TF32 || HALF) ? 2 : 4) gru_mm
     }
 }
 
-template <int FMT, int NT, bool HALF>
+template <int FMT, int NT, bool HALF, bool DEFER = false>
 cudaError_t launch_mma_one(const GruArgs& a, cudaStream_t st)
 {
+    if (HALF && !DEFER) {                  // one CTA per SM at most: the deferred-head form
+        static int sms[64] = {};
+        int dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && dev < 64) {
+            if (sms[dev] == 0) cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+            if (sms[dev] > 0 && (a.B + 3) / 4 <= sms[dev]) return launch_mma_one<FMT, NT, HALF, HALF>(a, st);
+        }
+    }
     using C = MmaCfg<FMT, NT>;
     static bool configured[64] = {};
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     if (dev < 64 && !configured[dev]) {
-        e = cudaFuncSetAttribute(gru_mma_kernel<FMT, NT, HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        e = cudaFuncSetAttribute(gru_mma_kernel<FMT, NT, HALF, false, DEFER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  C::SMEM_BYTES + 48 * 1024);
         if (e != cudaSuccess) return e;
         configured[dev] = true;
@@ -540,7 +567,7 @@ cudaError_t launch_mma_one(const GruArgs& a, cudaStream_t st)
             smem_bytes += (int)(rl * SC * 4);
         }
     }
-    gru_mma_kernel<FMT, NT, HALF><<<(unsigned)grid, 128, smem_bytes, st>>>(b);
+    gru_mma_kernel<FMT, NT, HALF, false, DEFER><<<(unsigned)grid, 128, smem_bytes, st>>>(b);
     ++g_launches;
     return cudaGetLastError();
 }
