@@ -12,7 +12,7 @@ from ntm_b200 import signals
 
 dev = "cuda:0"
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-for B, T, D in ((1, 480000, 365), (256, 1440000, 365), (1024, 1440000, 365), (1024, 1440000, 6000), (1023, 1440001, 365)):
+for B, T, D in ((1, 480000, 365), (256, 1440000, 365), (1024, 1440000, 365), (1024, 1440000, 2000), (1024, 1440000, 6000), (1023, 1440001, 365)):
     x = torch.randn(B, 1, T, device=dev)
     d = signals.delay_trajectory_device(B, T, dev).reshape(B, 1, T) * (D / 365.0)
     dl = ntm_b200.TimeVaryingDelayLine(max_delay=D)
