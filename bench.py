@@ -144,6 +144,28 @@ def run_reference(args, rank):
     }))
 
 
+def bind_to_gpu_numa_node(index):
+    """Multi-rank runs: pin this rank's threads (and so the first-touch placement of its pinned staging buffers) to the NUMA
+    node its GPU hangs off -- what `numactl --cpunodebind --membind` would do per rank.  Returns the node or None."""
+    try:
+        p = torch.cuda.get_device_properties(index)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -236,6 +258,7 @@ def main():
         avail = psutil.virtual_memory().available
         need = 2 * B * T * 4 * max(1, min(world, 8))          # pinned x and y of every rank on this host
         T_e = T if need < 0.5 * avail else max(FS, int(0.25 * avail / (8 * B * max(1, world))) // FS * FS)
+        numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 else None
         xh = torch.empty((B, 1, T_e), dtype=torch.float32, pin_memory=True)
         xh.copy_(x[:, :, :T_e])
         yh = torch.empty((B, 1, T_e), dtype=torch.float32, pin_memory=True)      # result buffer reused across steps
@@ -279,7 +302,8 @@ def main():
         "realtime_streams": value / FS,
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": B * T_e * 4,
                 "d2h_bytes_per_step": B * T_e * 4, "samples_per_stream": T_e, "finite": e2e_ok,
-                "api": "RNN.predict_host -> ntm_gru_predict_host (pinned host buffers)"},
+                "api": "RNN.predict_host -> ntm_gru_predict_host (pinned host buffers)",
+                "rank0_numa_node": numa_node},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {
