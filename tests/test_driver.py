@@ -174,3 +174,24 @@ def test_batched_evaluator_add_delay_equals_reference_style_chunk_loop(tmp_path)
             assert r["ESR"] == pytest.approx(float(ESRLoss()(out[:, :, 64:], td[:, :, 64:])), rel=1e-6)
     with pytest.raises(ValueError):
         driver.BatchedEvaluator(__import__("ntm_b200").DiffDelRNN(1, 64, 1, False, max_delay=8), delay=delay)
+
+
+def test_evaluator_trajectory_sources_and_errors(tmp_path):
+    """Host logic of the delay modes (no GPU): seconds -> samples like `meta['delay_trajectory'].float() * fs`
+    (code/test-model.py:349-351), file slicing by offset / length, and the error paths."""
+    t = np.linspace(0.004, 0.006, 1000)
+    tr = driver.BatchedEvaluator._trajectory
+    got = tr({"delay_trajectory": t}, 600, 44100)
+    assert got.dtype == torch.float32 and got.shape == (600,)
+    assert torch.equal(got, torch.from_numpy(t[:600].astype(np.float32)) * 44100.0)
+    p = str(tmp_path / "trajectory_3_.npy")
+    np.save(p, {"delay_trajectory": t})
+    seg = tr({"trajectory_file": p, "offset": 100, "length": 250}, 250, 48000)
+    assert torch.equal(seg, torch.from_numpy(t[100:350].astype(np.float32)) * 48000.0)
+    with pytest.raises(KeyError):
+        tr({"input_file": "x.wav"}, 10, 44100)
+    with pytest.raises(ValueError):
+        tr({"delay_trajectory": t[:5]}, 10, 44100)
+    from ntm_b200 import DiffDelRNN, TimeVaryingDelayLine
+    with pytest.raises(ValueError):                       # ADD_DELAY is a plain-GRU mode (code/test-model.py:354)
+        driver.BatchedEvaluator(DiffDelRNN(1, 64, 1, False, max_delay=8), delay=TimeVaryingDelayLine(max_delay=8))
