@@ -85,7 +85,10 @@ int run_gru(Handle* hd, int mode, const ntm::GruArgs& a, cudaStream_t st)
         const bool tcs_ok = fmt != 2 && a.d == nullptr;     // (tf32 operands exist only in the mma.sync kernel)
         const bool use_tcs = tcs_ok && (tg == 4 || (tg == 0 && a.B >= (long long)hd->sm_count * g_tcs_min_streams_per_sm));
         const bool use_mma = !use_tcs && (tg == 3 || tg == 4 || tg == 0 || fmt == 2);
-        if (use_tcs) {
+        if (tg == 5 && fmt != 2 && a.d == nullptr) {            // (n, 5): the 8-warp, 8-stream mma.sync form (gru_mma8.cu)
+            CU(ntm::launch_gru_mma8(a, fmt, st));
+            g_last_kernel = 4;
+        } else if (use_tcs) {
             CU(ntm::launch_gru_tcs(a, hd->tcs, fmt, hd->sm_count, tg == 4 ? (g_tune_s & 3) : 0, tg == 4 ? (g_tune_s >> 2) - 1 : -1, st));
             g_last_kernel = 3;
         } else if (use_mma) {

@@ -74,6 +74,7 @@ struct TcsConsts {
 // per-TU launchers -------------------------------------------------------------------------------
 cudaError_t launch_gru_fp32(const GruArgs& a, int sm_count, int tune_s, int tune_ks, int fast_act, cudaStream_t st);
 cudaError_t launch_gru_tc(const GruArgs& a, int fmt, int sm_count, int tune_n, int tune_g, cudaStream_t st);
+cudaError_t launch_gru_mma8(const GruArgs& a, int fmt, cudaStream_t st);     // 8 warps x 8 streams per CTA (gru_mma8.cu)
 cudaError_t launch_gru_tcs(const GruArgs& a, const TcsConsts& kc, int fmt, int sm_count, int tiles, int var, cudaStream_t st);
 void fill_tcs_consts(const float* blob_host, TcsConsts* kc);
 cudaError_t launch_gru_mma(const GruArgs& a, int fmt, int n_tiles, cudaStream_t st);

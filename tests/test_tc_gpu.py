@@ -51,8 +51,9 @@ def test_mode_mask():
 
 # kernel selectors (ntm_set_tuning): (n, 1|2) weight-stationary tcgen05 kernel, (n, 3) mma.sync kernel with n = 4, 8, 16
 # streams per CTA,
-# (tiles, 4) stream-major tcgen05 kernel (f16/bf16 operands; tf32 falls through to mma.sync)
-@pytest.mark.parametrize("kernel", [(32, 2), (8, 3), (4, 3), (1, 4), (2, 4)])
+# (tiles, 4) stream-major tcgen05 kernel (f16/bf16 operands; tf32 falls through to mma.sync), (8, 5) the 8-warp mma.sync
+# form of gru_mma8.cu (a recorded experiment, never dispatched automatically)
+@pytest.mark.parametrize("kernel", [(32, 2), (8, 3), (4, 3), (1, 4), (2, 4), (8, 5)])
 @pytest.mark.parametrize("mode", TC_MODES)
 @pytest.mark.parametrize("tag", ["cfg1", "cfg2"])
 def test_tc_predict_esr_vs_golden(tag, mode, kernel):
@@ -108,7 +109,7 @@ def test_tc_batch_vs_oracle_and_launch_shapes(mode):
                 assert float((m.predict(x[b:b + 1]) - y[b:b + 1]).abs().max()) <= 1e-6
 
 
-@pytest.mark.parametrize("kernel", [(0, 0), (32, 2), (64, 1), (8, 3), (4, 3), (1, 4), (2, 4)])
+@pytest.mark.parametrize("kernel", [(0, 0), (32, 2), (64, 1), (8, 3), (4, 3), (1, 4), (2, 4), (8, 5)])
 @pytest.mark.parametrize("mode", TC_MODES)
 def test_tc_segmentation_state_and_skip(mode, kernel):
     lib.load().ntm_set_tuning(*kernel)
