@@ -16,7 +16,11 @@ runs its own 1024 streams with no data-path collective (weak scaling); value = a
   roofline       contract asks for the tensor-pipe fraction: achieved = samples/s x 25088 FLOP (BASELINE.md
                  section 4) over the measured bf16 peak of MEASURED_PEAKS.json; extra keys give the honest bound of
                  the kernel that actually ran (fp32 FMA pipe / MUFU) and the (negligible) HBM rate
-  cpu_baseline   oracle/ref_torch.py (the reference's own torch.nn.GRU arithmetic) on the host cores, bounded sample
+  strict         the same workload (10 s of it) in the strict tensor-core mode "f16x3" (fp32-grade: max-abs <= 1e-5 against
+                 the reference like the CUDA-core fp32 mode), beside the f16-operand headline
+  cpu_baseline   the reference's own RNN class (code/model.py staged under baseline/_ref by baseline/stage_ref.py; the
+                 oracle's port of it if that is absent) on the host cores, bounded sample
+  aux.cfg4_strong  BASELINE.json configs[3]: 65 536 streams x 10 s sharded over the N ranks (strong scaling, no collective)
 """
 import argparse
 import json
@@ -28,6 +32,10 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+if "reference" in sys.argv[1:] and "--impl" in sys.argv[1:]:
+    # the reference arm is the reference's CPU path: code/model.py pins its tensors to "cuda" whenever torch sees one
+    # (code/model.py:61,223), so this process must not see the GPUs
+    os.environ["CUDA_VISIBLE_DEVICES"] = ""
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
@@ -97,50 +105,84 @@ class ClockSampler:
         return out
 
 
-def cpu_baseline(B, seg_count, threads):
-    """The reference's arithmetic (torch.nn.GRU + Linear on CPU, oracle/ref_torch.py) on a bounded sample:
-    forward over `seg_count` 2048-sample segments of B streams with the broadcast warm state."""
+def reference_runner():
+    """-> (run(x) -> y, kind, description): the reference's CPU arithmetic for a (B, 1, T) batch with predict() semantics per
+    stream.  kind "reference": the UNMODIFIED `RNN` class of code/model.py (staged under baseline/_ref, see
+    baseline/stage_ref.py) -- zero state, its own warm_start(), the batch-1 warm state broadcast to the B streams (the
+    reference's predict() itself only accepts B = 1), then its forward() over 2048-sample segments exactly
+    like the loop of RNN.predict (code/model.py:218-246).  kind "port": oracle/ref_torch.py, the same torch.nn.GRU + Linear
+    calls restated (used only if baseline/_ref is absent)."""
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    import stage_ref
+    if stage_ref.available():
+        refmodel = stage_ref.load_reference()
+        net = refmodel.RNN(input_size=1, hidden_size=64, output_size=1, skip=False)
+        net.load_state_dict(stage_ref.load_checkpoint("cfg2"))
+        net.eval()
+
+        def run(x):
+            B, T = x.shape[0], x.shape[2]
+            with torch.no_grad():
+                net.initialize_hidden()
+                net.warm_start()
+                net.hidden = net.hidden.expand(1, B, 64).contiguous()
+                out = torch.empty_like(x)
+                for s0 in range(0, T, 2048):
+                    out[:, :, s0:s0 + 2048] = net.forward(x[:, :, s0:s0 + 2048])
+            return out
+        return run, "reference", "code/model.py RNN (baseline/_ref, unmodified): warm_start + forward over 2048-sample segments"
     from oracle import ref_torch
+    net = ref_torch.RefNet(load_sd("cfg2"))
+    return (lambda x: net.predict(x)[0]), "port", "oracle/ref_torch.py (torch.nn.GRU + Linear restated; baseline/_ref not staged)"
+
+
+REF_SEGMENTS = 2          # 2048-sample segments per reference step (both the --impl reference arm and cpu_baseline)
+
+
+def cpu_baseline(B, seg_count, threads):
+    """The reference on the host cores over a bounded sample: `seg_count` 2048-sample segments of B streams."""
     from ntm_b200 import signals
     torch.set_num_threads(threads)
-    net = ref_torch.RefNet(load_sd("cfg2"))
+    run, kind, desc = reference_runner()
     T = 2048 * seg_count
     x = torch.from_numpy(signals.stream_batch(B, T, dur=60.0)).reshape(B, 1, T)
-    net.predict(x[:, :, :2048])                                  # warm-up of the MKL/oneDNN paths
+    run(x[:, :, :2048])                                          # warm-up of the MKL/oneDNN paths
     t0 = time.perf_counter()
-    net.predict(x)
+    run(x)
     dt = time.perf_counter() - t0
-    return B * T / dt, f"{B} streams x {T} samples ({seg_count} x 2048-sample segments), torch {torch.__version__}"
+    return B * T / dt, kind, f"{B} streams x {T} samples ({seg_count} x 2048-sample segments); {desc}; torch {torch.__version__}"
 
 
 def run_reference(args, rank):
-    """`--impl reference`: the reference's CPU path (its torch.nn.GRU arithmetic via oracle/ref_torch.py) with all
-    host threads, on a bounded sample of the same workload; rank 0 only."""
+    """`--impl reference`: the reference's own CPU path with all host threads, on a bounded sample of the same workload
+    (same streams, same checkpoint, the first REF_SEGMENTS x 2048 samples of every stream per step); rank 0 only."""
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    from oracle import ref_torch
     from ntm_b200 import signals
     torch.set_num_threads(threads)
-    net = ref_torch.RefNet(load_sd("cfg2"))
-    B, T = args.streams, 4096
+    run, kind, desc = reference_runner()
+    B, T = args.streams, 2048 * REF_SEGMENTS
     x = torch.from_numpy(signals.stream_batch(B, T, dur=60.0)).reshape(B, 1, T)
     for _ in range(args.warmup):
-        net.predict(x)
+        run(x)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        net.predict(x)
+        y = run(x)
     dt = time.perf_counter() - t0
     value = B * T * args.steps / dt
-    sample = f"{B} streams x {T} samples per step (bounded sample of the 60 s workload)"
+    sample = (f"{B} streams x {T} samples per step (bounded sample of the {args.seconds:g} s workload: the loop is stationary in "
+              f"time); {desc}")
     print(json.dumps({
         "impl": "reference", "metric": "GRU-HS64 samples/sec", "value": value, "unit": "samples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD.format(B=args.streams, sec=args.seconds), "sample": sample},
-        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
+        "config": {"workload": WORKLOAD.format(B=args.streams, sec=args.seconds), "sample": sample,
+                   "streams": B, "samples_per_stream_per_step": T, "same_config": False,
+                   "same_config_note": "same checkpoint, streams and signal generator; the CPU arm times a bounded sample"},
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "realtime_streams": value / FS,
+        "realtime_streams": value / FS, "checksum": float(y[:, :, ::257].double().sum()),
     }))
 
 
@@ -172,12 +214,13 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default="f16", choices=["fp32", "f16", "tf32", "bf16"])
+    ap.add_argument("--mode", default="f16", choices=["fp32", "f16", "f16x3", "strict", "tf32", "bf16"])
     ap.add_argument("--streams", type=int, default=1024)
     ap.add_argument("--seconds", type=float, default=60.0)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-aux", action="store_true", help="skip the batch-1 / large-batch side measurements")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cfg4", action="store_true", help="skip the 65 536-stream strong-scaling leg (aux.cfg4_strong)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -250,6 +293,7 @@ def main():
         kern_ms = sum(ev[2 + 2 * i].elapsed_time(ev[3 + 2 * i]) for i in range(args.steps)) / args.steps
         checksum = float(y[:, :, ::4801].double().sum())
         del y
+        model.static_io = False
         total_ms = sharding.max_over_ranks(total_ms, dev, dist)
         value = sharding.aggregate_rate(B * T * args.steps, world, total_ms * 1e-3)
 
@@ -273,10 +317,18 @@ def main():
         e2e_ok = bool(torch.isfinite(yh[:, :, ::4801]).all())
         del xh, yh
 
+        # ---- the same workload in the strict (fp32-grade) tensor-core mode, every rank its own shard ------------
+        strict = strict_leg(model, x, args, dev, barrier, sharding, dist, world, lib)
+        del x
+        # ---- BASELINE.json configs[3]: 65 536 streams x 10 s sharded over the ranks (strong scaling) ------------
+        cfg4 = None if args.no_cfg4 else cfg4_strong_leg(ntm_b200, signals, sharding, lib, dev, dist, rank, world, barrier, args.mode)
+
         # ---- side measurements (rank 0, outside the timed regions) -------------------------------------
         aux = {}
         if rank == 0 and not args.no_aux:
             aux = aux_measurements(ntm_b200, signals, dev, args.mode)
+        if cfg4 is not None:
+            aux["cfg4_strong"] = cfg4
 
     if rank != 0:
         if dist is not None:
@@ -294,7 +346,9 @@ def main():
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None,
         "dtype": {"fp32": "f32", "f16": "f16 operands, f32 accumulate/gates/state", "tf32": "tf32 operands, f32 accumulate/gates/state",
-                  "bf16": "bf16 operands, f32 accumulate/gates/state"}[args.mode],
+                  "bf16": "bf16 operands, f32 accumulate/gates/state",
+                  "f16x3": "f16 hi/lo operand pairs (3 MMAs per product, fp32-grade), f32 accumulate/gates/state",
+                  "strict": "f16 hi/lo operand pairs (3 MMAs per product, fp32-grade), f32 accumulate/gates/state"}[args.mode],
         "data": "synthetic",
         "config": {"workload": WORKLOAD.format(B=B, sec=args.seconds), "streams_per_gpu": B, "samples_per_stream": T,
                    "sample_rate": FS, "mode": args.mode, "parallelism": f"stream-sharded x{world}, no collective",
@@ -313,6 +367,7 @@ def main():
             # 395.3 MB read + 355.4 MB written for 1024 x 96 000 samples = 7.64 B per sample against 8 algorithmic -- the
             # last ~10 % of the y writes were still in the 126 MB L2 when the kernel ended), scaled to this launch
             "traffic": round(750.7e6 / (1024 * 96000) * B * T), "algorithmic_bytes": BYTES_PER_SAMPLE * B * T,
+            "traffic_source": "estimated_from_profile: bytes per sample of the ncu capture at 1024 x 96 000, scaled to this launch",
             "peak_source": peak_src,
             "kernel_ms": kern_ms, "kernel": kernel_name,
             "regime": "latency-bound recurrence: 1024 streams = 7 per SM, one dependent GRU step at a time (DESIGN.md section 4)",
@@ -324,16 +379,104 @@ def main():
             "mufu_bound_samples_per_s": sm_count * 16 * f_clk / 192,
             "hbm_gbs_achieved": sps_kernel * BYTES_PER_SAMPLE / 1e9, "hbm_frac": sps_kernel * BYTES_PER_SAMPLE / 1e9 / hbm_peak,
         },
+        "strict": strict,
         "checksum": checksum,
         "aux": aux,
     }
     if not args.no_cpu:
         threads = os.cpu_count() or 1
-        v, sample = cpu_baseline(min(B, 1024), 4, threads)
-        line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample}
+        v, kind, sample = cpu_baseline(min(B, 1024), REF_SEGMENTS, threads)
+        line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": threads, "kind": kind, "sample": sample}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
+
+
+def strict_leg(model, x, args, dev, barrier, sharding, dist, world, lib):
+    """The headline workload (its first 10 s) in the strict tensor-core mode: fp32-grade result (max-abs <= 1e-5 against the
+    reference, tests/test_parity_gpu.py STRICT_CLASS) from f16 hi/lo operand pairs, 3 MMAs per product.  Device-resident,
+    CUDA events, max over ranks, whole-job aggregate like `value`."""
+    B = x.shape[0]
+    Ts = min(x.shape[2], 10 * FS)
+    xs = x[:, :, :Ts]
+    prev = model.mode
+    model.mode = "f16x3"
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    try:
+        for _ in range(2):
+            model.predict(xs[:, :, :FS])
+        best = 1e30
+        for _ in range(2):
+            model.initialize_hidden()
+            model.warm_start()
+            model.hidden = model.hidden.expand(1, B, 64).contiguous()
+            barrier()
+            e0.record(); y = model(xs); e1.record()
+            torch.cuda.synchronize(dev)
+            best = min(best, sharding.max_over_ranks(e0.elapsed_time(e1), dev, dist))
+        kernel = lib.KERNEL_NAMES.get(lib.load().ntm_query(lib.Q_LAST_KERNEL), "?")
+        finite = bool(torch.isfinite(y[:, :, ::4801]).all())
+        del y
+    finally:
+        model.mode = prev
+    value = sharding.aggregate_rate(B * Ts, world, best * 1e-3)
+    tflops = value / world * 3 * FLOP_PER_SAMPLE / 1e12          # executed tensor FLOPs per GPU: three MMAs per product
+    peak = measured_peaks()[0]
+    return {"mode": "f16x3", "value": value, "unit": "samples/s", "kernel": kernel, "ns_per_timestep": best * 1e6 / Ts,
+            "samples_per_stream": Ts, "finite": finite, "tolerance": "fp32 class: max-abs <= 1e-5 vs the reference (tests)",
+            "executed_tensor_tflops_per_gpu": tflops, "frac_of_measured_bf16_peak": tflops / peak,
+            "algorithmic_frac": value / world * FLOP_PER_SAMPLE / 1e12 / peak}
+
+
+def cfg4_strong_leg(ntm_b200, signals, sharding, lib, dev, dist, rank, world, barrier, mode):
+    """BASELINE.json configs[3]: GRU-HS[64], 65 536 streams x 10 s, stream-sharded over the N ranks with no data-path
+    collective.  Rank r owns streams shard_range(65536, r, N) and walks the 10 s in time chunks with the state carried on the
+    device (the materialised signals would be 252 GB).  Inputs: per-stream synthetic signals generated on the device, four
+    distinct chunks cycled (resident before the timed region, as for `value`); every chunk launch reads and writes its own
+    1.6 GB of HBM, far beyond L2.  Timed with CUDA events over all launches of the pass, max over ranks."""
+    TOTAL, T10 = 65536, 10 * FS
+    lo, hi = sharding.shard_range(TOTAL, rank, world)
+    Bs = hi - lo
+    m = ntm_b200.RNN(1, 64, 1, False).to(dev)
+    m.load_state_dict(load_sd("cfg2"))
+    m.mode = mode
+    Tc = 3000
+    while Bs * Tc * 2 < 65536 * 3000 and Tc < 48000:       # ~0.8 GB per staged array whatever the shard size
+        Tc *= 2
+    nchunk = (T10 + Tc - 1) // Tc
+    xs = [signals.stream_batch_device(Bs, Tc, dev, first_stream=lo + 977 * k, dur=10.0).reshape(Bs, 1, Tc) for k in range(4)]
+    m.static_io = True                                      # y / state buffers reused across the chunk launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def one_pass():
+        m.initialize_hidden()
+        m.warm_start()
+        m.hidden = m.hidden.expand(1, Bs, 64).contiguous()
+        barrier()
+        e0.record()
+        done = 0
+        for k in range(nchunk):
+            n = min(Tc, T10 - done)
+            y = m(xs[k & 3] if n == Tc else xs[k & 3][:, :, :n])
+            done += n
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1), y
+
+    one_pass()
+    ms, y = one_pass()
+    kernel = lib.KERNEL_NAMES.get(lib.load().ntm_query(lib.Q_LAST_KERNEL), "?")
+    finite = bool(torch.isfinite(y[:, :, ::97]).all())
+    ms = sharding.max_over_ranks(ms, dev, dist)
+    value = TOTAL * T10 / (ms * 1e-3)
+    del xs, y, m
+    torch.cuda.empty_cache()
+    return {"workload": "cfg4: GRU-HS[64] 65 536 streams x 10 s, stream-sharded (strong scaling), time-chunked with carried state",
+            "value": value, "unit": "samples/s", "n_gpus": world, "scaling": "strong", "streams_per_gpu": Bs, "chunk_samples": Tc,
+            "chunks": nchunk, "ms": ms, "kernel": kernel, "mode": mode, "finite": finite, "realtime_streams": value / FS,
+            "per_gpu_samples_per_s": value / world,
+            "tensor_tflops_per_gpu": value / world * FLOP_PER_SAMPLE / 1e12,
+            "frac_of_measured_bf16_peak": value / world * FLOP_PER_SAMPLE / 1e12 / measured_peaks()[0]}
 
 
 def aux_measurements(ntm_b200, signals, dev, mode):
@@ -357,6 +500,38 @@ def aux_measurements(ntm_b200, signals, dev, mode):
         m1(x1[:, :, 64 * k:64 * k + 64])
     torch.cuda.synchronize(dev)
     out["batch1_block64_ns_per_sample_incl_launch"] = (time.perf_counter() - t0) * 1e9 / (nblk * 64)
+    # the same generic forward() with per-shape output buffers kept by the module (static_io), and captured in a CUDA Graph
+    # (SURVEY 8d cfg 5: the torch.ops entry points launch on PyTorch's current stream and allocate nothing)
+    for md in ("fp32", "f16"):
+        m1.mode = md
+        m1.static_io = True
+        m1.initialize_hidden(); m1.warm_start()
+        for k in range(50):
+            m1(x1[:, :, 64 * k:64 * k + 64])
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for k in range(nblk):
+            m1(x1[:, :, 64 * k:64 * k + 64])
+        torch.cuda.synchronize(dev)
+        out[f"batch1_block64_ns_per_sample_forward_static_io_{md}"] = (time.perf_counter() - t0) * 1e9 / (nblk * 64)
+        xs = torch.zeros((1, 1, 64), device=dev)
+        m1.initialize_hidden(); m1.warm_start()
+        m1.hidden = m1.hidden.clone()
+        m1(xs)                                   # state now lives in the module's static buffer (updated in place)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            yg = m1(xs)
+        for k in range(50):
+            xs.copy_(x1[:, :, 64 * k:64 * k + 64]); graph.replay()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for k in range(nblk):
+            xs.copy_(x1[:, :, 64 * k:64 * k + 64]); graph.replay()
+        torch.cuda.synchronize(dev)
+        out[f"batch1_block64_ns_per_sample_cuda_graph_{md}"] = (time.perf_counter() - t0) * 1e9 / (nblk * 64)
+        del graph, yg
+        m1.static_io = False
+    m1.mode = "fp32"
     # the same through the block-stream API (one C call per block), exact fp32 and f16 tensor-core arithmetic
     for md in ("fp32", "f16"):
         m1.mode = md
@@ -423,11 +598,9 @@ def aux_measurements(ntm_b200, signals, dev, mode):
     # the same 1024-stream workload (2 s of it) in every arithmetic mode, and the tcgen05 kernel forced
     x2 = signals.stream_batch_device(1024, 96000, dev, dur=60.0).reshape(1024, 1, 96000)
     per_mode = {}
-    for md in ("fp32", "f16", "tf32", "bf16"):
+    for md in ("fp32", "f16x3", "f16", "tf32", "bf16"):
         mb.mode = md
         per_mode[md] = timed(x2, mb)
-    mb.mode = "f16"
-    per_mode["f16_tcgen05_kernel"] = timed(x2, mb, (32, 2))
     out["cfg2_samples_per_s_by_mode"] = per_mode
     del x2
     # throughput regime (cfg 4 per-GPU widths): the three tensor-core kernels.  "auto" is what the dispatcher picks
@@ -439,9 +612,14 @@ def aux_measurements(ntm_b200, signals, dev, mode):
         xb = signals.stream_batch_device(Bb, Tb, dev, dur=10.0).reshape(Bb, 1, Tb)
         mb.mode = "f16"
         big[str(Bb)] = {"auto": timed(xb, mb), "auto_kernel": lib.KERNEL_NAMES.get(L.ntm_query(lib.Q_LAST_KERNEL), "?"),
-                        "mma_sync": timed(xb, mb, (8, 3)), "tcgen05_weight_stationary": timed(xb, mb, (32, 2))}
+                        "mma_sync": timed(xb, mb, (8, 3))}
         if Bb >= sms * 64:
             big[str(Bb)]["tcgen05_stream_major"] = timed(xb, mb, (2 if Bb > sms * 128 else 1, 4))
+        mb.mode = "f16x3"
+        big[str(Bb)]["strict_f16x3_auto"] = timed(xb, mb)
+        big[str(Bb)]["strict_f16x3_kernel"] = lib.KERNEL_NAMES.get(L.ntm_query(lib.Q_LAST_KERNEL), "?")
+        mb.mode = "tf32"
+        big[str(Bb)]["tf32_auto"] = timed(xb, mb)
         mb.mode = "fp32"
         big[str(Bb)]["fp32_cuda_core"] = timed(xb, mb)
         del xb

@@ -29,7 +29,7 @@ extern "C" {
 #pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden */
 #endif
 
-#define NTM_API_VERSION 1
+#define NTM_API_VERSION 2
 
 /* error codes */
 #define NTM_OK            0
@@ -46,7 +46,11 @@ extern "C" {
 #define NTM_MODE_FP32     0     /* fp32 FFMA on CUDA cores, libm-grade activations: the parity anchor */
 #define NTM_MODE_TF32     1     /* tensor cores, tf32 operands, fp32 accumulate */
 #define NTM_MODE_BF16     2     /* tensor cores, bf16 operands, fp32 accumulate (opt-in, lower accuracy) */
-#define NTM_MODE_TF32X3   3     /* tensor cores, 3xTF32 split (fp32-grade result) -- reserved, not built yet */
+#define NTM_MODE_F16X3    3     /* STRICT tensor-core mode, fp32-grade result (max-abs <= 1e-5 vs the reference, like
+                                   NTM_MODE_FP32): every operand is an f16 pair hi + lo'/2^11, three MMAs per product
+                                   (W_hi h_hi + W_hi h_lo + W_lo h_hi), fp32 accumulate -- the 3xTF32 scheme at half
+                                   the MMA count */
+#define NTM_MODE_TF32X3   NTM_MODE_F16X3   /* the name SURVEY.md section 8b reserved for the strict mode */
 #define NTM_MODE_F16      4     /* tensor cores, f16 operands (11-bit significand like tf32, half the MMAs), fp32 acc. */
 
 /* ntm_query selectors */
@@ -55,7 +59,8 @@ extern "C" {
 #define NTM_Q_SM_COUNT       2   /* of the current device */
 #define NTM_Q_MODE_MASK      3   /* bit m set <=> mode m is implemented */
 #define NTM_Q_KERNEL_LAUNCHES 4  /* number of engine kernels launched by this process so far */
-#define NTM_Q_LAST_KERNEL    5   /* recurrent kernel of the last launch: 0 fp32 CUDA-core, 1 mma.sync, 2 tcgen05 */
+#define NTM_Q_LAST_KERNEL    5   /* recurrent kernel of the process's last launch: 0 fp32 CUDA-core, 1 warp-level
+                                    mma.sync, 3 stream-major tcgen05 (per handle: ntm_handle_last_kernel) */
 
 int         ntm_query(int what);
 const char* ntm_strerror(int code);
@@ -69,6 +74,11 @@ int         ntm_last_cuda_error(void);
  */
 int  ntm_gru_prepare(const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
                      const float* w_out, const float* b_out, int H, int device, void** handle);
+/* Handles are reference counted: ntm_gru_prepare returns one reference, ntm_retain adds one, ntm_release (alias
+ * ntm_destroy) drops one and frees the device blob with the last.  An open real-time stream holds a reference, so
+ * releasing the model's handle under a live stream is safe. */
+int  ntm_retain(void* handle);
+void ntm_release(void* handle);
 void ntm_destroy(void* handle);
 
 /*
@@ -148,11 +158,22 @@ int ntm_diffdel_predict_host(void* handle, int mode, const float* x_host, const 
                              float* y_host, float* pre_d_host, float* h_host, float* hist_host,
                              int64_t B, int64_t T, int64_t D, int skip, int64_t chunk_T);
 
-/* Tuning knob for experiments and tests (0, 0 = automatic dispatch).  fp32 kernel: streams per CTA / k-split.
- * Tensor-core modes, by the second argument: 1|2 weight-stationary tcgen05 kernel (first = streams per group 32|64),
- * 3 warp-level mma.sync kernel (first = streams per CTA 8|16), 4 stream-major tcgen05 kernel (first = 128-stream
- * tiles per CTA 1|2, + 4 * (variant + 1) for kernel variants).  Process-global, not thread-safe. */
+/* Per-row variant: sums is DEVICE memory for B x 2 doubles; row b is evaluated over its own window of samples
+ * [first[b], first[b] + count[b]) (DEVICE int64 arrays of B values; NULL = 0 / T), clipped to the row -- ragged batches and
+ * the reference's INIT_LEN cut (code/test-model.py:323-325,367-370: the DC filter starts from zero state at the cut) in
+ * ONE launch.  loss_b = (sums[b][0]/n_b) / (sums[b][1]/n_b + 1e-5). */
+int ntm_esr_sums_rows(const float* out, int64_t ldo, const float* target, int64_t ldt, int64_t B, int64_t T,
+                      const int64_t* first, const int64_t* count, int dc_pre, double* sums, int device, void* stream);
+
+/* Kernel-selection knob for experiments and tests (0, 0 = automatic dispatch).  fp32 kernel: streams per CTA / k-split.
+ * Tensor-core modes, by the second argument: 3 warp-level mma.sync kernel (first = streams per CTA 4|8|16),
+ * 4 stream-major tcgen05 kernel (first = 128-stream tiles per CTA 1|2,
+ * + 4 * (variant + 1) for kernel variants).  ntm_set_tuning sets the process-wide default (one atomic word, safe to
+ * call concurrently with launches); ntm_handle_set_tuning overrides it for one handle (streams_per_cta = -1: follow the
+ * default again).  ntm_handle_last_kernel: NTM_Q_LAST_KERNEL of that handle's last launch. */
 int ntm_set_tuning(int streams_per_cta, int ksplit);
+int ntm_handle_set_tuning(void* handle, int streams_per_cta, int ksplit);
+int ntm_handle_last_kernel(void* handle);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

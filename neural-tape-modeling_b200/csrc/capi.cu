@@ -1,5 +1,7 @@
 // extern "C" launch layer: the drop-in boundary declared in include/ntm_b200.h.
 // No torch types, no exceptions, no hidden allocation on the device-pointer entry points.
+#include <atomic>
+#include <mutex>
 #include <new>
 #include <string.h>
 #include <time.h>
@@ -8,17 +10,25 @@
 #include "ntm_common.cuh"
 
 namespace ntm {
-unsigned long long g_launches = 0;
+std::atomic<unsigned long long> g_launches{0};
 }
 
 namespace {
 
 constexpr unsigned HANDLE_MAGIC = 0x4e544d42u;   // "NTMB"
 thread_local int t_last_cuda = 0;
-int g_tune_s = 0, g_tune_ks = 0, g_tune_fast = 0;
-// 0 fp32 CUDA-core, 1 warp-level mma.sync, 2 tcgen05 weight-stationary, 3 tcgen05 stream-major (NTM_Q_LAST_KERNEL)
-int g_last_kernel = -1;
-long long g_tcs_min_streams_per_sm = 110;     // crossover mma.sync -> stream-major tcgen05 kernel
+// Kernel-selection knob (experiments / tests): a process-wide default (ntm_set_tuning) that a handle may override
+// (ntm_handle_set_tuning).  Packed into one atomic word so that concurrent launches from several threads read a
+// consistent pair; nothing on the launch path writes shared state except the two counters below.
+struct Tuning {
+    int s = 0, ks = 0;
+};
+std::atomic<unsigned long long> g_tuning{0};
+unsigned long long pack_tuning(int s, int ks) { return ((unsigned long long)(unsigned)s << 32) | (unsigned)ks; }
+Tuning unpack_tuning(unsigned long long v) { return Tuning{(int)(v >> 32), (int)(v & 0xffffffffull)}; }
+// 0 fp32 CUDA-core, 1 warp-level mma.sync, 3 tcgen05 stream-major (NTM_Q_LAST_KERNEL; also kept per handle)
+std::atomic<int> g_last_kernel{-1};
+constexpr long long TCS_MIN_STREAMS_PER_SM = 110;     // crossover mma.sync -> stream-major tcgen05 kernel
 
 struct HostPipe {            // staging of the *_host entry points
     cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
@@ -36,6 +46,9 @@ struct Handle {
     float* blob;
     ntm::TcsConsts tcs;      // host copy of the stream-major kernel's constant-bank parameters
     HostPipe pipe;
+    std::atomic<int> refs{1};                        // ntm_gru_prepare's reference + one per ntm_retain / open real-time stream
+    std::atomic<unsigned long long> tuning{~0ull};   // ~0: follow the process-wide default
+    std::atomic<int> last_kernel{-1};
 };
 
 int cuda_fail(cudaError_t e)
@@ -48,6 +61,14 @@ int cuda_fail(cudaError_t e)
         cudaError_t e_ = (call);                   \
         if (e_ != cudaSuccess) return cuda_fail(e_); \
     } while (0)
+
+constexpr int MAX_DEVICES = 64;
+struct CheckCtx {            // ntm_delay_check: persistent result flag of one device
+    std::mutex mu;
+    int* dev_flag = nullptr;
+    int* host_flag = nullptr;
+};
+CheckCtx g_check[MAX_DEVICES];
 
 struct DeviceGuard {
     int prev = -1;
@@ -66,42 +87,48 @@ Handle* as_handle(void* p)
     return (h && h->magic == HANDLE_MAGIC) ? h : nullptr;
 }
 
-constexpr int MODE_MASK = (1 << NTM_MODE_FP32) | (1 << NTM_MODE_TF32) | (1 << NTM_MODE_BF16) | (1 << NTM_MODE_F16);
+constexpr int MODE_MASK = (1 << NTM_MODE_FP32) | (1 << NTM_MODE_TF32) | (1 << NTM_MODE_BF16) | (1 << NTM_MODE_F16) |
+                          (1 << NTM_MODE_F16X3);
+// operand format selector of the tensor-core launchers (tc_prims.cuh FMT_*)
+int mode_fmt(int mode) { return mode == NTM_MODE_TF32 ? 2 : mode == NTM_MODE_BF16 ? 1 : mode == NTM_MODE_F16X3 ? 3 : 0; }
 bool mode_supported(int mode) { return mode >= 0 && mode < 31 && ((MODE_MASK >> mode) & 1); }
 
 int run_gru(Handle* hd, int mode, const ntm::GruArgs& a, cudaStream_t st)
 {
     if (!mode_supported(mode)) return NTM_EUNSUPPORTED;
+    unsigned long long tv = hd->tuning.load(std::memory_order_relaxed);
+    if (tv == ~0ull) tv = g_tuning.load(std::memory_order_relaxed);
+    const Tuning tune = unpack_tuning(tv);
+    int kernel;
     if (mode == NTM_MODE_FP32) {
-        CU(ntm::launch_gru_fp32(a, hd->sm_count, g_tune_s, g_tune_ks & 0xff, g_tune_fast, st));
-        g_last_kernel = 0;
+        // fp32 kernel: (streams per CTA, k-split); bit 8 of the second value selects the MUFU-approx activations (experiment)
+        CU(ntm::launch_gru_fp32(a, hd->sm_count, tune.s, tune.ks & 0xff, (tune.ks >> 8) & 1, st));
+        kernel = 0;
     } else {
-        const int fmt = mode == NTM_MODE_TF32 ? 2 : mode == NTM_MODE_BF16 ? 1 : 0;    // tc_prims.cuh FMT_*
-        // latency regime (few streams per SM): warp-level mma.sync kernel; throughput regime (>= one 128-stream tile
-        // per SM, plain GRU, 16-bit operands): stream-major tcgen05 kernel.
-        // ntm_set_tuning(n, 3) forces mma.sync with n/8 tiles per CTA, (n, 1|2) the weight-stationary tcgen05 kernel,
-        // (tiles + 4 * (variant + 1), 4) the stream-major tcgen05 kernel with 1 or 2 tiles per CTA (variant: experiments).
-        const int tg = g_tune_ks & 0xff;
-        const bool tcs_ok = fmt != 2 && a.d == nullptr;     // (tf32 operands exist only in the mma.sync kernel)
-        const bool use_tcs = tcs_ok && (tg == 4 || (tg == 0 && a.B >= (long long)hd->sm_count * g_tcs_min_streams_per_sm));
-        const bool use_mma = !use_tcs && (tg == 3 || tg == 4 || tg == 0 || fmt == 2);
-        if (tg == 5 && fmt != 2 && a.d == nullptr) {            // (n, 5): the 8-warp, 8-stream mma.sync form (gru_mma8.cu)
-            CU(ntm::launch_gru_mma8(a, fmt, st));
-            g_last_kernel = 4;
-        } else if (use_tcs) {
-            CU(ntm::launch_gru_tcs(a, hd->tcs, fmt, hd->sm_count, tg == 4 ? (g_tune_s & 3) : 0, tg == 4 ? (g_tune_s >> 2) - 1 : -1, st));
-            g_last_kernel = 3;
-        } else if (use_mma) {
-            // tuning (n, 3): n = 4 / 8 / 16 streams per CTA; automatic: 4 (shorter dependent step) up to two such CTAs
-            // per SM -- measured 231 vs 241 ns/step at 1024 streams, 197 vs 245 at <= 592 (profiles/r01_mma_half_check.txt)
-            const int nt = g_tune_s > 0 && tg == 3 ? g_tune_s / 8 : (a.B <= 8ll * hd->sm_count ? 0 : 1);
-            CU(ntm::launch_gru_mma(a, fmt, nt, st));
-            g_last_kernel = 1;
+        const int fmt = mode_fmt(mode);
+        // latency regime (few streams per SM): warp-level mma.sync kernel; throughput regime (>= one 128-stream tile per
+        // SM): stream-major tcgen05 kernel (every operand format; DiffDelRNN batches run the delay read as a second pass).
+        // Tuning (n, 3) forces mma.sync with n = 4 | 8 | 16 streams per CTA, (tiles + 4 * (variant + 1), 4) the
+        // stream-major kernel with 1 or 2 tiles per CTA.
+        const int tg = tune.ks & 0xff;
+        const bool use_tcs = tg == 4 || (tg == 0 && a.B >= (long long)hd->sm_count * TCS_MIN_STREAMS_PER_SM);
+        if (use_tcs) {
+            CU(ntm::launch_gru_tcs(a, hd->tcs, fmt, hd->sm_count, tg == 4 ? (tune.s & 3) : 0, tg == 4 ? (tune.s >> 2) - 1 : -1, st));
+            kernel = 3;
         } else {
-            CU(ntm::launch_gru_tc(a, fmt, hd->sm_count, tg ? g_tune_s : 0, tg, st));
-            g_last_kernel = 2;
+            // automatic: 4 streams per CTA (shorter dependent step) up to two such CTAs per SM -- measured 221 vs 243
+            // ns/step at 1024 streams, 177 vs 238 at <= 592 (profiles/r02_g2_check.txt); the strict form is tensor-pipe
+            // bound and wastes nothing on dead columns beyond one CTA per SM
+            int nt;
+            if (tune.s > 0 && tg == 3) nt = tune.s / 8;
+            else if (fmt == 3) nt = a.B <= 4ll * hd->sm_count ? 0 : 1;
+            else nt = a.B <= 8ll * hd->sm_count ? 0 : 1;
+            CU(ntm::launch_gru_mma(a, fmt, nt, st));
+            kernel = 1;
         }
     }
+    hd->last_kernel.store(kernel, std::memory_order_relaxed);
+    g_last_kernel.store(kernel, std::memory_order_relaxed);
     return NTM_OK;
 }
 
@@ -186,7 +213,7 @@ int predict_host(Handle* hd, int mode, const float* x_host, const float* d_host,
         CU(cudaStreamWaitEvent(p.s_run, p.ev_in[k], 0));
         if (c >= 2) CU(cudaStreamWaitEvent(p.s_run, p.ev_out[k], 0));
         ntm::GruArgs a{};
-        a.blob = hd->blob; a.x = dx[k]; a.y = dy[k]; a.h_in = dh; a.h_out = dh;
+        a.blob = hd->blob; a.sm_count = hd->sm_count; a.x = dx[k]; a.y = dy[k]; a.h_in = dh; a.h_out = dh;
         a.B = B; a.T = n; a.ldx = C; a.ldy = C; a.skip = skip;
         if (delay) {
             a.d = dd[k]; a.ldd = C; a.pre = dp[k]; a.ldp = C; a.D = (int)D;
@@ -237,8 +264,8 @@ int ntm_query(int what)
             return n;
         }
         case NTM_Q_MODE_MASK: return MODE_MASK;
-        case NTM_Q_KERNEL_LAUNCHES: return (int)(ntm::g_launches & 0x7fffffffull);
-        case NTM_Q_LAST_KERNEL: return g_last_kernel;
+        case NTM_Q_KERNEL_LAUNCHES: return (int)(ntm::g_launches.load() & 0x7fffffffull);
+        case NTM_Q_LAST_KERNEL: return g_last_kernel.load();
         default: return NTM_EINVAL;
     }
 }
@@ -263,10 +290,22 @@ int ntm_last_cuda_error(void) { return t_last_cuda; }
 int ntm_set_tuning(int streams_per_cta, int ksplit)
 {
     if (streams_per_cta < 0 || ksplit < 0) return NTM_EINVAL;
-    g_tune_s = streams_per_cta;
-    g_tune_ks = ksplit & 0xff;
-    g_tune_fast = (ksplit >> 8) & 1;      // experiment: bit 8 selects the MUFU-approx activations
+    g_tuning.store(pack_tuning(streams_per_cta, ksplit), std::memory_order_relaxed);
     return NTM_OK;
+}
+
+int ntm_handle_set_tuning(void* handle, int streams_per_cta, int ksplit)
+{
+    Handle* hd = as_handle(handle);
+    if (!hd || streams_per_cta < -1 || ksplit < 0) return NTM_EINVAL;
+    hd->tuning.store(streams_per_cta < 0 ? ~0ull : pack_tuning(streams_per_cta, ksplit), std::memory_order_relaxed);
+    return NTM_OK;
+}
+
+int ntm_handle_last_kernel(void* handle)
+{
+    Handle* hd = as_handle(handle);
+    return hd ? hd->last_kernel.load(std::memory_order_relaxed) : NTM_EINVAL;
 }
 
 int ntm_gru_prepare(const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, const float* w_out,
@@ -319,10 +358,21 @@ int ntm_gru_prepare(const float* w_ih, const float* w_hh, const float* b_ih, con
     return NTM_OK;
 }
 
-void ntm_destroy(void* handle)
+int ntm_retain(void* handle)
+{
+    Handle* hd = as_handle(handle);
+    if (!hd) return NTM_EINVAL;
+    hd->refs.fetch_add(1, std::memory_order_relaxed);
+    return NTM_OK;
+}
+
+void ntm_destroy(void* handle) { ntm_release(handle); }
+
+void ntm_release(void* handle)
 {
     Handle* hd = as_handle(handle);
     if (!hd) return;
+    if (hd->refs.fetch_sub(1, std::memory_order_acq_rel) > 1) return;      // an open real-time stream / a retained user
     DeviceGuard g(hd->device);
     HostPipe& p = hd->pipe;
     if (p.ready) {
@@ -357,7 +407,7 @@ int ntm_gru_forward(void* handle, int mode, const float* x, int64_t ldx, float* 
     if (T == 0) return copy_state(h_in, h_out, B, (cudaStream_t)stream);
     if (!x || !y || ldx < T || ldy < T) return NTM_EINVAL;
     ntm::GruArgs a{};
-    a.blob = hd->blob; a.x = x; a.y = y; a.h_in = h_in; a.h_out = h_out;
+    a.blob = hd->blob; a.sm_count = hd->sm_count; a.x = x; a.y = y; a.h_in = h_in; a.h_out = h_out;
     a.B = B; a.T = T; a.ldx = ldx; a.ldy = ldy; a.skip = skip;
     return run_gru(hd, mode, a, (cudaStream_t)stream);
 }
@@ -380,7 +430,7 @@ int ntm_diffdel_forward(void* handle, int mode, const float* x, int64_t ldx, con
     }
     if (!x || !d || !y || !pre_d || ldx < T || ldd < T || ldy < T || ldp < T || y == pre_d) return NTM_EINVAL;
     ntm::GruArgs a{};
-    a.blob = hd->blob; a.x = x; a.y = y; a.h_in = h_in; a.h_out = h_out; a.d = d; a.pre = pre_d;
+    a.blob = hd->blob; a.sm_count = hd->sm_count; a.x = x; a.y = y; a.h_in = h_in; a.h_out = h_out; a.d = d; a.pre = pre_d;
     a.hist_in = hist_in; a.hist_out = hist_out;
     a.B = B; a.T = T; a.ldx = ldx; a.ldy = ldy; a.ldd = ldd; a.ldp = ldp;
     a.D = (int)D; a.warmup = warmup; a.skip = skip;
@@ -405,20 +455,25 @@ int ntm_delay_check(const float* d, int64_t ldd, int64_t B, int64_t T, int64_t D
 {
     if (B < 0 || T < 0 || D < 0) return NTM_EINVAL;
     if (B == 0 || T == 0) return NTM_OK;
-    if (!d || ldd < T) return NTM_EINVAL;
+    if (!d || ldd < T || device < 0 || device >= MAX_DEVICES) return NTM_EINVAL;
     DeviceGuard g(device);
     if (!g.ok) return cuda_fail(cudaErrorInvalidDevice);
-    int* flag = nullptr;
-    CU(cudaMalloc(&flag, sizeof(int)));
-    int host_flag = 0;
-    cudaError_t e = cudaMemsetAsync(flag, 0, sizeof(int), (cudaStream_t)stream);
-    if (e == cudaSuccess) e = ntm::launch_delay_check(d, ldd, B, T, D, flag, (cudaStream_t)stream);
-    if (e == cudaSuccess)
-        e = cudaMemcpyAsync(&host_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
-    cudaFree(flag);
-    if (e != cudaSuccess) return cuda_fail(e);
-    return host_flag ? NTM_EDELAY : NTM_OK;
+    // one persistent flag pair per device (device int + page-locked host int), created on first use: no allocation, no
+    // cudaFree (a device-wide synchronisation) on the call path; the mutex serialises concurrent checks on one device
+    // (the call synchronises its stream anyway)
+    CheckCtx& c = g_check[device];
+    std::lock_guard<std::mutex> lock(c.mu);
+    if (!c.dev_flag) {
+        CU(cudaMalloc(&c.dev_flag, sizeof(int)));
+        cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&c.host_flag), sizeof(int), cudaHostAllocDefault);
+        if (e != cudaSuccess) { cudaFree(c.dev_flag); c.dev_flag = nullptr; return cuda_fail(e); }
+    }
+    *c.host_flag = 0;
+    CU(cudaMemsetAsync(c.dev_flag, 0, sizeof(int), (cudaStream_t)stream));
+    CU(ntm::launch_delay_check(d, ldd, B, T, D, c.dev_flag, (cudaStream_t)stream));
+    CU(cudaMemcpyAsync(c.host_flag, c.dev_flag, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    return *c.host_flag ? NTM_EDELAY : NTM_OK;
 }
 
 // ---- real-time streams: a resident server kernel fed through a mapped host mailbox --------------------------------
@@ -453,8 +508,10 @@ void rt_free(RtStream* r)
     if (r->st) cudaStreamDestroy(r->st);
     if (r->h_dev) cudaFree(r->h_dev);
     if (r->mb) cudaFreeHost(r->mb);
+    Handle* hd = r->hd;
     r->magic = 0;
     delete r;
+    ntm_release(hd);
 }
 
 }  // namespace
@@ -474,6 +531,7 @@ int ntm_rt_open(void* handle, int mode, const float* h_host, int64_t B, int64_t 
     if (!g.ok) return cuda_fail(cudaErrorInvalidDevice);
     RtStream* r = new (std::nothrow) RtStream();
     if (!r) return NTM_ENOMEM;
+    hd->refs.fetch_add(1, std::memory_order_relaxed);        // the resident kernel reads the handle's blob until close
     r->magic = RT_MAGIC; r->hd = hd; r->B = (int)B; r->T = (int)block_len; r->mb = nullptr; r->h_dev = nullptr;
     r->st = nullptr; r->seq = 0; r->dead = false;
     cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&r->mb), sizeof(ntm::RtMailbox), cudaHostAllocMapped);
@@ -489,11 +547,10 @@ int ntm_rt_open(void* handle, int mode, const float* h_host, int64_t B, int64_t 
     if (e == cudaSuccess) e = cudaHostGetDevicePointer(reinterpret_cast<void**>(&mb_dev), r->mb, 0);
     if (e == cudaSuccess) {
         ntm::GruArgs a{};
-        a.blob = hd->blob; a.x = &mb_dev->x[0][0]; a.y = &mb_dev->y[0][0]; a.h_in = r->h_dev; a.h_out = r->h_dev;
+        a.blob = hd->blob; a.sm_count = hd->sm_count; a.x = &mb_dev->x[0][0]; a.y = &mb_dev->y[0][0]; a.h_in = r->h_dev; a.h_out = r->h_dev;
         a.B = B; a.T = block_len; a.ldx = ntm::RT_MAXBLK; a.ldy = ntm::RT_MAXBLK; a.skip = skip;
         a.rt = mb_dev; a.rt_idle_ns = (unsigned long long)idle_timeout_ms * 1000000ull;
-        const int fmt = mode == NTM_MODE_TF32 ? 2 : mode == NTM_MODE_BF16 ? 1 : 0;
-        e = ntm::launch_gru_mma_rt(a, fmt, r->st);
+        e = ntm::launch_gru_mma_rt(a, mode_fmt(mode), r->st);
     }
     if (e != cudaSuccess) { rt_free(r); return cuda_fail(e); }
     *rt = r;
@@ -551,6 +608,21 @@ int ntm_esr_sums(const float* out, int64_t ldo, const float* target, int64_t ldt
     int sms = 0;
     CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
     CU(ntm::launch_esr(out, ldo, target, ldt, B, T, dc_pre, sums, sms, (cudaStream_t)stream));
+    return NTM_OK;
+}
+
+int ntm_esr_sums_rows(const float* out, int64_t ldo, const float* target, int64_t ldt, int64_t B, int64_t T,
+                      const int64_t* first, const int64_t* count, int dc_pre, double* sums, int device, void* stream)
+{
+    if (B < 0 || T < 0 || (B > 0 && !sums)) return NTM_EINVAL;
+    if (B > 0 && T > 0 && (!out || !target || ldo < T || ldt < T)) return NTM_EINVAL;
+    if (B == 0) return NTM_OK;
+    DeviceGuard g(device);
+    if (!g.ok) return cuda_fail(cudaErrorInvalidDevice);
+    int sms = 0;
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    CU(ntm::launch_esr(out, ldo, target, ldt, B, T, dc_pre, sums, sms, (cudaStream_t)stream,
+                       reinterpret_cast<const long long*>(first), reinterpret_cast<const long long*>(count), 1));
     return NTM_OK;
 }
 

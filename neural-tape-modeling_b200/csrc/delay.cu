@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(256) delay_check_kernel(const float* __restric
     bool bad = false;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < T;
          t += (long long)gridDim.x * blockDim.x)
-        bad |= d[b * ldd + t] > Dmax;
+        bad |= !(d[b * ldd + t] <= Dmax);      // (NaN trips the check like the reference's assert, code/model.py:283)
     if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(flag, 1);
 }
 

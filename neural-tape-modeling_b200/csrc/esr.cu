@@ -50,16 +50,25 @@ template <bool DCPRE>
 __global__ void __launch_bounds__(32 * esr_warps(DCPRE)) esr_kernel(const float* __restrict__ out, long long ldo,
                                                              const float* __restrict__ tgt, long long ldt, long long B,
                                                              long long T, long long chunk, long long chunks, double R,
-                                                             double Rw /* R^(ESR_TAPS-1) */, double* __restrict__ sums)
+                                                             double Rw /* R^(ESR_TAPS-1) */, double* __restrict__ sums,
+                                                             const long long* __restrict__ first,
+                                                             const long long* __restrict__ count, int per_row)
 {
     const int lane = threadIdx.x & 31;
     constexpr int W = DCPRE ? 1 : 4;                     // = esr_warps(DCPRE)
     const long long item = DCPRE ? (long long)blockIdx.x : (long long)blockIdx.x * W + (threadIdx.x >> 5);
     if (item >= B * chunks) return;
     const long long b = item / chunks, c = item % chunks;
+    // per-row window [first[b], first[b] + count[b]): the row simply starts there (the DC pre-emphasis of the reference is
+    // applied to the CUT signals, zero-padded in front: code/test-model.py:367-370), clipped to the row
+    long long f0 = first ? first[b] : 0;
+    f0 = f0 < 0 ? 0 : (f0 > T ? T : f0);
+    if (count) { const long long n = count[b]; T = n < 0 ? 0 : (n < T - f0 ? n : T - f0); } else { T -= f0; }
     const long long c0 = c * chunk, c1 = (c0 + chunk) < T ? (c0 + chunk) : T;
-    const float* __restrict__ o = out + b * ldo;
-    const float* __restrict__ t = tgt + b * ldt;
+    if (c0 >= T) return;
+    const float* __restrict__ o = out + b * ldo + f0;
+    const float* __restrict__ t = tgt + b * ldt + f0;
+    if (per_row) sums += 2 * b;
     double num = 0.0, den = 0.0;
 
     if (!DCPRE) {
@@ -212,11 +221,13 @@ __global__ void __launch_bounds__(32 * esr_warps(DCPRE)) esr_kernel(const float*
 
 }  // namespace
 
-// sums[0] = sum (f(t) - f(o))^2, sums[1] = sum f(t)^2 over B x T (sums is zeroed here, on the stream).
+// sums[0] = sum (f(t) - f(o))^2, sums[1] = sum f(t)^2 over B x T (sums is zeroed here, on the stream); per_row: one pair per
+// row over its own window (BatchedEvaluator scores a whole ragged batch in one launch).
 cudaError_t launch_esr(const float* out, long long ldo, const float* tgt, long long ldt, long long B, long long T,
-                       int dc_pre, double* sums, int sm_count, cudaStream_t st)
+                       int dc_pre, double* sums, int sm_count, cudaStream_t st, const long long* first, const long long* count,
+                       int per_row)
 {
-    cudaError_t e = cudaMemsetAsync(sums, 0, 2 * sizeof(double), st);
+    cudaError_t e = cudaMemsetAsync(sums, 0, (per_row ? (size_t)(B > 0 ? B : 0) * 2 : 2) * sizeof(double), st);
     if (e != cudaSuccess || B <= 0 || T <= 0) return e;
     // chunk: enough work items to fill the GPU (>= ~8 warps per SM sub-partition) but long against the warm-up
     long long chunk = dc_pre ? 65536 : 16384;      // (the plain pass has no warm-up to amortise; shorter items balance better)
@@ -228,8 +239,8 @@ cudaError_t launch_esr(const float* out, long long ldo, const float* tgt, long l
     const double R = 0.995;
     double Rw = 1.0;
     for (int i = 0; i < ESR_TAPS - 1; ++i) Rw *= R;
-    if (dc_pre) esr_kernel<true><<<(unsigned)grid, 32 * esr_warps(true), 0, st>>>(out, ldo, tgt, ldt, B, T, chunk, chunks, R, Rw, sums);
-    else esr_kernel<false><<<(unsigned)grid, 32 * esr_warps(false), 0, st>>>(out, ldo, tgt, ldt, B, T, chunk, chunks, R, Rw, sums);
+    if (dc_pre) esr_kernel<true><<<(unsigned)grid, 32 * esr_warps(true), 0, st>>>(out, ldo, tgt, ldt, B, T, chunk, chunks, R, Rw, sums, first, count, per_row);
+    else esr_kernel<false><<<(unsigned)grid, 32 * esr_warps(false), 0, st>>>(out, ldo, tgt, ldt, B, T, chunk, chunks, R, Rw, sums, first, count, per_row);
     ++g_launches;
     return cudaGetLastError();
 }

@@ -94,6 +94,48 @@ __device__ __forceinline__ float ex2_poly(float x)
     return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
 
+// ---- strict (fp32-grade) activations ---------------------------------------------------------------------------------
+// MUFU ex2.approx / rcp.approx are accurate to ~2 ulp, but their error is SYSTEMATIC: a constant relative bias of 1 ulp in
+// the gate values moves the output of the cfg-2 checkpoint by 1.7e-5 (numpy emulation), a random +-2 ulp only by 2e-6 --
+// the recurrence integrates a bias.  The strict mode therefore evaluates 2^x with a degree-6 minimax polynomial on the FMA
+// pipe (max relative error 0.66 ulp, mean bias 0.002 ulp over the reduced range) and refines the reciprocal with one
+// Newton step (error <= 1 ulp, unbiased).
+__device__ __forceinline__ float ex2_strict(float x)
+{
+    x = fmaxf(x, -125.0f);
+    const float t = x + 12582912.0f;                 // 1.5 * 2^23: round-to-nearest integer part in the low mantissa bits
+    const float f = x - (t - 12582912.0f);           // [-0.5, 0.5]
+    float p = 1.534580806e-04f;
+    p = fmaf(p, f, 1.339993090e-03f);
+    p = fmaf(p, f, 9.618489072e-03f);
+    p = fmaf(p, f, 5.550328642e-02f);
+    p = fmaf(p, f, 2.402264625e-01f);
+    p = fmaf(p, f, 6.931471825e-01f);
+    p = fmaf(p, f, 1.0f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+__device__ __forceinline__ float rcp_strict(float d)
+{
+    const float r = rcp_approx(d);
+    return fmaf(r, fmaf(-d, r, 1.0f), r);
+}
+#ifndef NTM_STRICT_ACT
+#define NTM_STRICT_ACT 1          // 0: bare MUFU, 1: Newton reciprocal (the default, see below), 2: + polynomial 2^x
+#endif
+__device__ __forceinline__ float ex2_s(float x) { return NTM_STRICT_ACT >= 2 ? ex2_strict(x) : ex2_approx(x); }
+__device__ __forceinline__ float rcp_s(float d) { return NTM_STRICT_ACT >= 1 ? rcp_strict(d) : rcp_approx(d); }
+
+// One (unit, stream) pair in the strict mode: own reciprocals everywhere (nothing shared, no products of denominators).
+// pr, pz: complete scaled pre-activations of r and z; ahn = W_hn h + b_hn, gin = W_in x + b_in (scaled); returns the new state.
+__device__ __forceinline__ float gates_strict(float pr, float pz, float ahn, float gin, float h)
+{
+    const float r = rcp_s(1.0f + ex2_s(fminf(pr, EX2_CLAMP)));
+    const float dn = 1.0f + ex2_s(fminf(fmaf(r, ahn, gin), EX2_CLAMP));
+    const float z = rcp_s(1.0f + ex2_s(fminf(pz, EX2_CLAMP)));
+    const float n = fmaf(-2.0f, rcp_s(dn), 1.0f);
+    return fmaf(z, h - n, n);
+}
+
 // Two hidden units (0, 1) of ONE stream, complete pre-activations (see gates_rz_dn_pre), new states out.
 //   SHARE4: one reciprocal serves r and z of BOTH units (4.0 MUFU per unit-step instead of 4.5); the ex2 arguments of
 //           r, z are then clamped to 30 so that the product of four denominators stays below 2^121 (sigmoid saturates

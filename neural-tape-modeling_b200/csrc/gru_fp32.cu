@@ -284,16 +284,11 @@ template <int KS, int S, bool FAST>
 cudaError_t launch_one(const GruArgs& a, cudaStream_t st)
 {
     using C = Cfg<KS, S>;
-    static bool configured[64] = {};     // per device
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
+    static OncePerDevice once;
+    cudaError_t e = once.run([] {
+        return cudaFuncSetAttribute(gru_fp32_kernel<KS, S, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    });
     if (e != cudaSuccess) return e;
-    if (dev < 64 && !configured[dev]) {
-        e = cudaFuncSetAttribute(gru_fp32_kernel<KS, S, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 C::SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-        configured[dev] = true;
-    }
     const long long grid = (a.B + S - 1) / S;
     gru_fp32_kernel<KS, S, FAST><<<(unsigned)grid, C::NT, C::SMEM_BYTES, st>>>(a);
     ++g_launches;

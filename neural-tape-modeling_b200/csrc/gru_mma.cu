@@ -31,13 +31,21 @@ namespace {
 
 constexpr float LOG2E_F = 1.4426950408889634f;
 
-template <int FMT>
+// SPLIT (f16 only): the strict, fp32-grade mode.  Every operand is carried as two f16 numbers, v = hi + lo' / 2^11 with
+// hi = f16(v) and lo' = f16((v - hi) * 2^11) (the power-of-two scaling keeps lo' a NORMAL f16 number down to |v| ~ 2^-25,
+// so the pair holds 22 significand bits like 3xTF32 does, at half the MMA count), and the contraction is evaluated as
+//     W h  ~=  W_hi h_hi  +  2^-11 (W_hi h_lo' + W_lo' h_hi)            (the dropped W_lo h_lo term is ~2^-22 relative)
+// with fp32 accumulation: three MMAs where the rounded-operand modes issue one.
+template <int FMT, bool SPLIT = false>
 struct Frag {
     static constexpr int ELT = FMT == FMT_TF32 ? 4 : 2;
     static constexpr int NK = FMT == FMT_TF32 ? 8 : 4;            // MMAs along K = 64
-    static constexpr int ROW_BYTES = 64 * ELT + 16;               // padded row of the state tile (conflict-free stores)
-    static constexpr int BW = 16 * ELT / 4;                       // 32-bit words of B fragments per thread and n-tile
+    static constexpr int NP = SPLIT ? 2 : 1;                      // operand parts (hi, lo')
+    static constexpr int PART_BYTES = 64 * ELT;                   // one part of a stream's state row
+    static constexpr int ROW_BYTES = NP * PART_BYTES + 16;        // padded row of the state tile (conflict-free stores)
+    static constexpr int BW = 16 * ELT / 4;                       // 32-bit words of B fragments per thread, n-tile and part
 };
+constexpr float SPLIT_SCALE = 2048.0f, SPLIT_INV = 1.0f / 2048.0f;
 
 template <int FMT>
 __device__ __forceinline__ void mma_sync(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
@@ -68,19 +76,28 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi)
 }
 
 // rounded states of the adjacent units (unit, unit + 1) of one stream; unit is even
-template <int FMT>
+template <int FMT, bool SPLIT = false>
 __device__ __forceinline__ void store_state2(uint8_t* row, int unit, float v0, float v1)
 {
-    if (FMT == FMT_TF32) *reinterpret_cast<uint2*>(row + unit * 4) = make_uint2(to_tf32(v0), to_tf32(v1));
-    else *reinterpret_cast<uint32_t*>(row + unit * 2) = pack2<FMT>(v0, v1);
+    if (FMT == FMT_TF32) {
+        *reinterpret_cast<uint2*>(row + unit * 4) = make_uint2(to_tf32(v0), to_tf32(v1));
+    } else if (SPLIT) {       // hi part, then the scaled residual 128 bytes further (Frag::PART_BYTES)
+        const __half2 hi = __floats2half2_rn(v0, v1);
+        const float2 hf = __half22float2(hi);
+        const __half2 lo = __floats2half2_rn((v0 - hf.x) * SPLIT_SCALE, (v1 - hf.y) * SPLIT_SCALE);
+        *reinterpret_cast<uint32_t*>(row + unit * 2) = *reinterpret_cast<const uint32_t*>(&hi);
+        *reinterpret_cast<uint32_t*>(row + 128 + unit * 2) = *reinterpret_cast<const uint32_t*>(&lo);
+    } else {
+        *reinterpret_cast<uint32_t*>(row + unit * 2) = pack2<FMT>(v0, v1);
+    }
 }
 
-template <int FMT, int NT>
+template <int FMT, int NT, bool SPLIT = false>
 struct MmaCfg {
     static constexpr int S = 8 * NT;                 // streams per CTA
     static constexpr int CH = 128;                   // steps per staged chunk (measured at 1024 streams: 32 -> 232.7 ns/step, 64 -> 238, 128 -> 221.7, 256 -> 220.1)
     static constexpr int YP_LD = S + 2;              // even: float2 stores of the head partials
-    static constexpr int HB_BYTES = S * Frag<FMT>::ROW_BYTES;
+    static constexpr int HB_BYTES = S * Frag<FMT, SPLIT>::ROW_BYTES;
     static constexpr int OFF_HB = 0;                               // [2][S][ROW_BYTES]
     static constexpr int OFF_XS = (2 * HB_BYTES + 127) / 128 * 128;   // [2][CH][S] floats
     static constexpr int OFF_YP = OFF_XS + 2 * CH * S * 4;         // [4 warps][CH][YP_LD] floats
@@ -96,17 +113,21 @@ struct MmaCfg {
 // costs two PCIe round trips instead of a kernel launch, a prologue and a stream synchronisation.
 // DEFER (HALF only): the output head's accumulators are consumed one iteration later (see the head block); wins when a
 // warp has its SM sub-partition to itself (one CTA per SM: cfg 3, cfg 5, the real-time server), loses otherwise.
-template <int FMT, int NT, bool HALF, bool RT = false, bool DEFER = RT>
-// (HALF is only dispatched up to two CTAs per SM: the full register file removes its spills, 197 vs 204 ns/step)
-__global__ void __launch_bounds__(128, (FMT == FMT_TF32 || HALF) ? 2 : 4) gru_mma_kernel(const GruArgs a)
+template <int FMT, int NT, bool HALF, bool RT = false, bool DEFER = RT, bool SPLIT = false>
+// (HALF is only dispatched up to two CTAs per SM: the full register file removes its spills, 197 vs 204 ns/step; the
+// strict form keeps two sets of weight fragments in registers)
+__global__ void __launch_bounds__(128, (FMT == FMT_TF32 || HALF || SPLIT) ? 2 : 4) gru_mma_kernel(const GruArgs a)
 {
     static_assert(!HALF || NT == 1, "HALF needs a single n8 tile");
     static_assert(!RT || HALF, "the real-time server uses the 4-streams-per-CTA form");
+    static_assert(!SPLIT || (FMT == FMT_F16 && NT == 1 && !DEFER), "the strict form: f16 pairs, one n8 tile, immediate head");
+    constexpr int NP = SPLIT ? 2 : 1;                // operand parts (hi, lo')
+    constexpr int SL = SPLIT ? 1 : 0;                // accumulators per tile: W_hi h_hi | (strict) W_hi h_lo' , W_lo' h_hi
     constexpr int SC = HALF ? 4 : 8 * NT;            // streams per CTA
     constexpr int CS = HALF ? 2 : 1;                 // column stride of a stream
     constexpr int NE = HALF ? 1 : 2;                 // live columns per thread and n8 tile
-    using C = MmaCfg<FMT, NT>;
-    using F = Frag<FMT>;
+    using C = MmaCfg<FMT, NT, SPLIT>;
+    using F = Frag<FMT, SPLIT>;
     constexpr int S = C::S, CH = C::CH, NK = F::NK, BW = F::BW;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* const hb = smem + C::OFF_HB;
@@ -127,7 +148,7 @@ __global__ void __launch_bounds__(128, (FMT == FMT_TF32 || HALF) ? 2 : 4) gru_mm
     // a thread's B fragments of a whole step are plain vector loads from the state tile
     //   f16/bf16: thread tig consumes elements tig*16 + 4ks + {0,1 | 2,3} in k-step ks
     //   tf32:     thread tig consumes elements (ks/2)*16 + tig*4 + 2(ks%2) + {0 | 1}
-    uint32_t areg[3][NK][4];
+    uint32_t areg[NP][3][NK][4];
     {
         const float sc_rz = -LOG2E_F, sc_n = 2.0f * LOG2E_F;
         const float* wr0 = blob + BlobLayout::W_HH + (0 * 64 + u0) * 64;
@@ -145,16 +166,24 @@ __global__ void __launch_bounds__(128, (FMT == FMT_TF32 || HALF) ? 2 : 4) gru_mm
             for (int ks = 0; ks < NK; ++ks) {
                 if (FMT == FMT_TF32) {
                     const int k = (ks >> 1) * 16 + tig * 4 + 2 * (ks & 1);
-                    areg[tile][ks][0] = to_tf32(slo[tile] * lo[tile][k]);
-                    areg[tile][ks][1] = to_tf32(shi[tile] * hi[tile][k]);
-                    areg[tile][ks][2] = to_tf32(slo[tile] * lo[tile][k + 1]);
-                    areg[tile][ks][3] = to_tf32(shi[tile] * hi[tile][k + 1]);
+                    areg[0][tile][ks][0] = to_tf32(slo[tile] * lo[tile][k]);
+                    areg[0][tile][ks][1] = to_tf32(shi[tile] * hi[tile][k]);
+                    areg[0][tile][ks][2] = to_tf32(slo[tile] * lo[tile][k + 1]);
+                    areg[0][tile][ks][3] = to_tf32(shi[tile] * hi[tile][k + 1]);
                 } else {
                     const int k = tig * 16 + 4 * ks;
-                    areg[tile][ks][0] = pack2<FMT>(slo[tile] * lo[tile][k], slo[tile] * lo[tile][k + 1]);
-                    areg[tile][ks][1] = pack2<FMT>(shi[tile] * hi[tile][k], shi[tile] * hi[tile][k + 1]);
-                    areg[tile][ks][2] = pack2<FMT>(slo[tile] * lo[tile][k + 2], slo[tile] * lo[tile][k + 3]);
-                    areg[tile][ks][3] = pack2<FMT>(shi[tile] * hi[tile][k + 2], shi[tile] * hi[tile][k + 3]);
+                    // fragment register i: a0 (row gid, k..k+1) a1 (row gid+8, k..k+1) a2 (row gid, k+2..k+3) a3 (row gid+8, ..)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float* row = (i & 1) ? hi[tile] : lo[tile];
+                        const float sc = (i & 1) ? shi[tile] : slo[tile];
+                        const float w0 = sc * row[k + 2 * (i >> 1)], w1 = sc * row[k + 2 * (i >> 1) + 1];
+                        areg[0][tile][ks][i] = pack2<FMT>(w0, w1);
+                        if (SPLIT) {
+                            const float2 wh = __half22float2(__floats2half2_rn(w0, w1));
+                            areg[NP - 1][tile][ks][i] = pack2<FMT>((w0 - wh.x) * SPLIT_SCALE, (w1 - wh.y) * SPLIT_SCALE);
+                        }
+                    }
                 }
             }
     }
@@ -166,8 +195,12 @@ __global__ void __launch_bounds__(128, (FMT == FMT_TF32 || HALF) ? 2 : 4) gru_mm
     // contracted with the SAME B fragments, i.e. with the rounded state of the previous step, K split over the four
     // warps (warp w takes k-steps w*NK/4 ..), and lands in c0..c3 of the lanes gid == 0: y(2tig) = c0 + c2, y(2tig+1) =
     // c1 + c3.  The four warps' partial sums are added at the chunk flush.
+    // Strict form: row 0 = w_hi and row 8 = w_lo' are contracted with the hi part of the state, a second fragment (row 0 =
+    // 0, row 8 = w_hi) with its lo' part INTO THE SAME accumulators: c0, c1 = w_hi h_hi and c2, c3 = w_lo' h_hi + w_hi h_lo',
+    // y = c0 + 2^-11 c2.
     constexpr int HK = NK / 4;
     uint32_t ahead[HK][4];
+    uint32_t ahead2[SPLIT ? 2 : 1] = {};             // a1, a3 of the second fragment (a0 = a2 = 0)
 #pragma unroll
     for (int q = 0; q < HK; ++q) {
         const int ks = warp * HK + q;
@@ -179,39 +212,57 @@ __global__ void __launch_bounds__(128, (FMT == FMT_TF32 || HALF) ? 2 : 4) gru_mm
             if (FMT == FMT_TF32) hi[i] = __uint_as_float(to_tf32(w[i]));
             else if (FMT == FMT_BF16) hi[i] = __bfloat162float(__float2bfloat16_rn(w[i]));
             else hi[i] = __half2float(__float2half_rn(w[i]));
-            lo[i] = w[i] - hi[i];
+            lo[i] = SPLIT ? (w[i] - hi[i]) * SPLIT_SCALE : w[i] - hi[i];
         }
         if (FMT == FMT_TF32) {      // a0 (row 0, k) a1 (row 8, k) a2 (row 0, k+1) a3 (row 8, k+1)
             ahead[q][0] = to_tf32(hi[0]); ahead[q][1] = to_tf32(lo[0]); ahead[q][2] = to_tf32(hi[1]); ahead[q][3] = to_tf32(lo[1]);
         } else {                    // a0 (row 0, k..k+1) a1 (row 8, k..k+1) a2 (row 0, k+2..k+3) a3 (row 8, k+2..k+3)
             ahead[q][0] = pack2<FMT>(hi[0], hi[1]); ahead[q][1] = pack2<FMT>(lo[0], lo[1]);
             ahead[q][2] = pack2<FMT>(hi[2], hi[3]); ahead[q][3] = pack2<FMT>(lo[2], lo[3]);
+            if (SPLIT) { ahead2[0] = ahead[q][0]; ahead2[SPLIT ? 1 : 0] = ahead[q][2]; }
         }
     }
     // this warp's k-steps of the B fragments (warp-uniform selects; a dynamic index would spill the array)
-    auto head_mma = [&](const uint32_t (&b)[BW], float (&c)[4]) {
+    auto head_mma = [&](const uint32_t (&bp)[NP][BW], float (&c)[4]) {
         c[0] = c[1] = c[2] = c[3] = 0.0f;
 #pragma unroll
         for (int q = 0; q < HK; ++q) {
-            uint32_t b0, b1;
-            if (HK == 1) {
-                b0 = (warp & 2) ? ((warp & 1) ? b[6] : b[4]) : ((warp & 1) ? b[2] : b[0]);
-                b1 = (warp & 2) ? ((warp & 1) ? b[7] : b[5]) : ((warp & 1) ? b[3] : b[1]);
-            } else {
-                b0 = (warp & 2) ? ((warp & 1) ? b[12 + 2 * q] : b[8 + 2 * q]) : ((warp & 1) ? b[4 + 2 * q] : b[2 * q]);
-                b1 = (warp & 2) ? ((warp & 1) ? b[13 + 2 * q] : b[9 + 2 * q]) : ((warp & 1) ? b[5 + 2 * q] : b[1 + 2 * q]);
+#pragma unroll
+            for (int part = 0; part < NP; ++part) {
+                const uint32_t (&b)[BW] = bp[part];
+                uint32_t b0, b1;
+                if (HK == 1) {
+                    b0 = (warp & 2) ? ((warp & 1) ? b[6] : b[4]) : ((warp & 1) ? b[2] : b[0]);
+                    b1 = (warp & 2) ? ((warp & 1) ? b[7] : b[5]) : ((warp & 1) ? b[3] : b[1]);
+                } else {
+                    b0 = (warp & 2) ? ((warp & 1) ? b[12 + 2 * q] : b[8 + 2 * q]) : ((warp & 1) ? b[4 + 2 * q] : b[2 * q]);
+                    b1 = (warp & 2) ? ((warp & 1) ? b[13 + 2 * q] : b[9 + 2 * q]) : ((warp & 1) ? b[5 + 2 * q] : b[1 + 2 * q]);
+                }
+                if (part == 0) {
+                    mma_sync<FMT>(c, ahead[q], b0, b1);
+                } else {
+                    const uint32_t a2[4] = {0u, ahead2[0], 0u, ahead2[NP - 1]};
+                    mma_sync<FMT>(c, a2, b0, b1);
+                }
             }
-            mma_sync<FMT>(c, ahead[q], b0, b1);
         }
     };
-    auto load_bfrag = [&](const uint8_t* tile, int nt, uint32_t (&b)[BW]) {
+    // the two columns of a head tile -> the samples of streams 2tig, 2tig + 1
+    auto head_value = [&](const float (&c)[4]) {
+        return SPLIT ? make_float2(fmaf(SPLIT_INV, c[2], c[0]), fmaf(SPLIT_INV, c[3], c[1])) : make_float2(c[0] + c[2], c[1] + c[3]);
+    };
+    auto load_bfrag = [&](const uint8_t* tile, int nt, uint32_t (&bp)[NP][BW]) {
         // f16/bf16: the thread's 16 elements are contiguous (2 vectors); tf32: vector q holds elements
-        // q*16 + tig*4 .. +3 (4 vectors, a quarter-warp reads 64 contiguous bytes)
-        const uint8_t* src = tile + (nt * 8 + gid) * F::ROW_BYTES + (FMT == FMT_TF32 ? tig * 16 : tig * 32);
+        // q*16 + tig*4 .. +3 (4 vectors, a quarter-warp reads 64 contiguous bytes); strict form: the lo' part of the row
+        // follows the hi part
 #pragma unroll
-        for (int q = 0; q < BW / 4; ++q) {
-            const uint4 v = *reinterpret_cast<const uint4*>(src + q * (FMT == FMT_TF32 ? 64 : 16));
-            b[4 * q] = v.x; b[4 * q + 1] = v.y; b[4 * q + 2] = v.z; b[4 * q + 3] = v.w;
+        for (int part = 0; part < NP; ++part) {
+            const uint8_t* src = tile + (nt * 8 + gid) * F::ROW_BYTES + part * F::PART_BYTES + (FMT == FMT_TF32 ? tig * 16 : tig * 32);
+#pragma unroll
+            for (int q = 0; q < BW / 4; ++q) {
+                const uint4 v = *reinterpret_cast<const uint4*>(src + q * (FMT == FMT_TF32 ? 64 : 16));
+                bp[part][4 * q] = v.x; bp[part][4 * q + 1] = v.y; bp[part][4 * q + 2] = v.z; bp[part][4 * q + 3] = v.w;
+            }
         }
     };
 
@@ -266,8 +317,8 @@ __global__ void __launch_bounds__(128, (FMT == FMT_TF32 || HALF) ? 2 : 4) gru_mm
             const bool live = col % CS == 0 && s < ns;
 #pragma unroll
             for (int u = 0; u < 2; ++u) hst[nt][u][e] = (live && a.h_in) ? a.h_in[(b0 + s) * 64 + u0 + u] : 0.0f;
-            store_state2<FMT>(hb + col * F::ROW_BYTES, u0, hst[nt][0][e], hst[nt][1][e]);
-            store_state2<FMT>(hb + C::HB_BYTES + col * F::ROW_BYTES, u0, 0.0f, 0.0f);     // dead columns stay finite
+            store_state2<FMT, SPLIT>(hb + col * F::ROW_BYTES, u0, hst[nt][0][e], hst[nt][1][e]);
+            store_state2<FMT, SPLIT>(hb + C::HB_BYTES + col * F::ROW_BYTES, u0, 0.0f, 0.0f);     // dead columns stay finite
         }
     const long long nchunks = (a.T + CH - 1) / CH;
     int cur = 0;
@@ -326,12 +377,18 @@ __global__ void __launch_bounds__(128, (FMT == FMT_TF32 || HALF) ? 2 : 4) gru_mm
             const uint8_t* hcur = hb + cur * C::HB_BYTES;
             uint8_t* hnext = hb + (cur ^ 1) * C::HB_BYTES;
             float acc[NT][3][4];
-            uint32_t breg[NT][BW];
+            float accs[SPLIT ? NT : 1][3][SPLIT ? 2 : 1][4];      // strict form: W_hi h_lo' and W_lo' h_hi (scaled by 2^11)
+            uint32_t breg[NT][NP][BW];
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) {
                 load_bfrag(hcur, nt, breg[nt]);
 #pragma unroll
-                for (int tile = 0; tile < 3; ++tile) acc[nt][tile][0] = acc[nt][tile][1] = acc[nt][tile][2] = acc[nt][tile][3] = 0.0f;
+                for (int tile = 0; tile < 3; ++tile) {
+                    acc[nt][tile][0] = acc[nt][tile][1] = acc[nt][tile][2] = acc[nt][tile][3] = 0.0f;
+                    if (SPLIT)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) accs[nt][tile][0][i] = accs[nt][tile][SL][i] = 0.0f;
+                }
                 if (!HALF) {
                     // throughput form: input projection and biases enter through the accumulators (fewer FP32 instructions
                     // after the MMAs: 976 vs 1027 ns/step at 8192 streams; the 4-stream latency form measured slower with it)
@@ -350,19 +407,25 @@ __global__ void __launch_bounds__(128, (FMT == FMT_TF32 || HALF) ? 2 : 4) gru_mm
             // n tiles alternate (two dependent accumulator chains keep the pipe busy), the z tile follows and overlaps r's
             // gate math.  (Measured 233.7 vs 239.1 ns/step at 1024 streams against the ks-outer order over tiles that mixed
             // r and z rows; splitting z into two half-K chains gained nothing; bit-identical results.)
+            // Strict form: three independent accumulator chains per tile (hi.hi, hi.lo', lo'.hi), issued r, n, then z; the
+            // scaled chains are folded into the main accumulator once all MMAs are in flight.
+            auto tile_mmas = [&](int tile, int ks) {
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    mma_sync<FMT>(acc[nt][tile], areg[0][tile][ks], breg[nt][0][2 * ks], breg[nt][0][2 * ks + 1]);
+                    if (SPLIT) {
+                        mma_sync<FMT>(accs[nt][tile][0], areg[0][tile][ks], breg[nt][NP - 1][2 * ks], breg[nt][NP - 1][2 * ks + 1]);
+                        mma_sync<FMT>(accs[nt][tile][SL], areg[NP - 1][tile][ks], breg[nt][0][2 * ks], breg[nt][0][2 * ks + 1]);
+                    }
+                }
+            };
             {
 #pragma unroll
             for (int ks = 0; ks < NK; ++ks)
 #pragma unroll
-                for (int tile = 0; tile < 3; tile += 2)
+                for (int tile = 0; tile < 3; tile += 2) tile_mmas(tile, ks);
 #pragma unroll
-                    for (int nt = 0; nt < NT; ++nt)
-                        mma_sync<FMT>(acc[nt][tile], areg[tile][ks], breg[nt][2 * ks], breg[nt][2 * ks + 1]);
-#pragma unroll
-            for (int ks = 0; ks < NK; ++ks)
-#pragma unroll
-                for (int nt = 0; nt < NT; ++nt)
-                    mma_sync<FMT>(acc[nt][1], areg[1][ks], breg[nt][2 * ks], breg[nt][2 * ks + 1]);
+            for (int ks = 0; ks < NK; ++ks) tile_mmas(1, ks);
             }
 
             // ---- head of the PREVIOUS step from the same B fragments (see `ahead`) -------------------------------
@@ -376,15 +439,13 @@ __global__ void __launch_bounds__(128, (FMT == FMT_TF32 || HALF) ? 2 : 4) gru_mm
             for (int nt = 0; nt < NT; ++nt) {
                 if (DEFER) {
                     if (tt > 1 && gid == 0)
-                        *reinterpret_cast<float2*>(yp + (warp * CH + tt - 2) * C::YP_LD + nt * 8 + 2 * tig) =
-                            make_float2(hpend[nt][0] + hpend[nt][2], hpend[nt][1] + hpend[nt][3]);
+                        *reinterpret_cast<float2*>(yp + (warp * CH + tt - 2) * C::YP_LD + nt * 8 + 2 * tig) = head_value(hpend[nt]);
                     head_mma(breg[nt], hpend[nt]);
                 } else {
                     float ch[4];
                     head_mma(breg[nt], ch);
                     if (tt > 0 && gid == 0)
-                        *reinterpret_cast<float2*>(yp + (warp * CH + tt - 1) * C::YP_LD + nt * 8 + 2 * tig) =
-                            make_float2(ch[0] + ch[2], ch[1] + ch[3]);
+                        *reinterpret_cast<float2*>(yp + (warp * CH + tt - 1) * C::YP_LD + nt * 8 + 2 * tig) = head_value(ch);
                 }
             }
             // ---- gates, state blend, rounded state for the next step, head partials ------------------------------
@@ -392,10 +453,33 @@ __global__ void __launch_bounds__(128, (FMT == FMT_TF32 || HALF) ? 2 : 4) gru_mm
             for (int nt = 0; nt < NT; ++nt) {
                 const float2 xv = *reinterpret_cast<const float2*>(xcur + tt * S + nt * 8 + 2 * tig);
                 float z[2][2], dn[2][2], hn[2][2];
+                if (SPLIT) {                       // fold the scaled chains: W h = hi.hi + 2^-11 (hi.lo' + lo'.hi)
+#pragma unroll
+                    for (int tile = 0; tile < 3; ++tile)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            if (!HALF || (i & 1) == 0)
+                                acc[nt][tile][i] = fmaf(SPLIT_INV, accs[nt][tile][0][i] + accs[nt][tile][SL][i], acc[nt][tile][i]);
+                }
+                if (SPLIT) {                       // strict activations (gates.cuh), nothing shared between pairs
+#pragma unroll
+                    for (int u = 0; u < 2; ++u)
+#pragma unroll
+                        for (int e = 0; e < NE; ++e) {
+                            const float xx = e ? xv.y : xv.x;
+                            float pr = acc[nt][0][2 * u + e], pz = acc[nt][1][2 * u + e], ahn = acc[nt][2][2 * u + e];
+                            if (HALF) {            // (non-HALF: the accumulators already hold W_i x + b for r, z and b_hn for n)
+                                pr += fmaf(uc[u].cr_w, xx, uc[u].cr_b);
+                                pz += fmaf(uc[u].cz_w, xx, uc[u].cz_b);
+                                ahn += uc[u].ch_b;
+                            }
+                            hn[u][e] = gates_strict(pr, pz, ahn, fmaf(uc[u].cn_w, xx, uc[u].cn_b), hst[nt][u][e]);
+                        }
+                }
 #pragma unroll
                 for (int u = 0; u < 2; ++u)
 #pragma unroll
-                    for (int e = 0; e < NE; ++e) {
+                    for (int e = 0; e < (SPLIT ? 0 : NE); ++e) {
                         // r has its own reciprocal at every width: sharing 1/(d_r d_z) (4.5 instead of 5.5 MUFU per pair)
                         // measured slower even in the throughput regime (1052 vs 1030 ns/step at 8192 streams)
                         const float xx = e ? xv.y : xv.x;
@@ -409,7 +493,7 @@ __global__ void __launch_bounds__(128, (FMT == FMT_TF32 || HALF) ? 2 : 4) gru_mm
                         }
                     }
 #pragma unroll
-                for (int e = 0; e < NE; ++e) {
+                for (int e = 0; e < (SPLIT ? 0 : NE); ++e) {
                     if (HALF) {                    // own n-gate reciprocals, shorter dependent chain (sharing them between the two
                                                    // units measured 227.3 vs 221.5 ns/step even with two CTAs per SM)
                         hn[0][e] = gates_blend1(z[0][e], dn[0][e], hst[nt][0][e]);
@@ -422,7 +506,7 @@ __global__ void __launch_bounds__(128, (FMT == FMT_TF32 || HALF) ? 2 : 4) gru_mm
                 for (int e = 0; e < NE; ++e) {
                     hst[nt][0][e] = hn[0][e];
                     hst[nt][1][e] = hn[1][e];
-                    store_state2<FMT>(hnext + (nt * 8 + 2 * tig + e) * F::ROW_BYTES, u0, hn[0][e], hn[1][e]);
+                    store_state2<FMT, SPLIT>(hnext + (nt * 8 + 2 * tig + e) * F::ROW_BYTES, u0, hn[0][e], hn[1][e]);
                 }
             }
             cur ^= 1;
@@ -433,15 +517,13 @@ __global__ void __launch_bounds__(128, (FMT == FMT_TF32 || HALF) ? 2 : 4) gru_mm
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) {
                 if (DEFER && n > 1 && gid == 0) // (the pending head of the step before it)
-                    *reinterpret_cast<float2*>(yp + (warp * CH + n - 2) * C::YP_LD + nt * 8 + 2 * tig) =
-                        make_float2(hpend[nt][0] + hpend[nt][2], hpend[nt][1] + hpend[nt][3]);
-                uint32_t bfin[BW];
+                    *reinterpret_cast<float2*>(yp + (warp * CH + n - 2) * C::YP_LD + nt * 8 + 2 * tig) = head_value(hpend[nt]);
+                uint32_t bfin[NP][BW];
                 float ch[4];
                 load_bfrag(hb + cur * C::HB_BYTES, nt, bfin);
                 head_mma(bfin, ch);
                 if (gid == 0)
-                    *reinterpret_cast<float2*>(yp + (warp * CH + n - 1) * C::YP_LD + nt * 8 + 2 * tig) =
-                        make_float2(ch[0] + ch[2], ch[1] + ch[3]);
+                    *reinterpret_cast<float2*>(yp + (warp * CH + n - 1) * C::YP_LD + nt * 8 + 2 * tig) = head_value(ch);
             }
             __syncthreads();
         }
@@ -523,28 +605,19 @@ __global__ void __launch_bounds__(128, (FMT == FMT_TF32 || HALF) ? 2 : 4) gru_mm
     }
 }
 
-template <int FMT, int NT, bool HALF, bool DEFER = false>
+template <int FMT, int NT, bool HALF, bool DEFER = false, bool SPLIT = false>
 cudaError_t launch_mma_one(const GruArgs& a, cudaStream_t st)
 {
-    if (HALF && !DEFER) {                  // one CTA per SM at most: the deferred-head form
-        static int sms[64] = {};
-        int dev = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess && dev < 64) {
-            if (sms[dev] == 0) cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
-            if (sms[dev] > 0 && (a.B + 3) / 4 <= sms[dev]) return launch_mma_one<FMT, NT, HALF, HALF>(a, st);
-        }
+    if (HALF && !DEFER && !SPLIT) {        // one CTA per SM at most: the deferred-head form
+        if (a.sm_count > 0 && (a.B + 3) / 4 <= a.sm_count) return launch_mma_one<FMT, NT, HALF, HALF>(a, st);
     }
-    using C = MmaCfg<FMT, NT>;
-    static bool configured[64] = {};
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
+    using C = MmaCfg<FMT, NT, SPLIT>;
+    static OncePerDevice once;
+    cudaError_t e = once.run([] {
+        return cudaFuncSetAttribute(gru_mma_kernel<FMT, NT, HALF, false, DEFER, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    C::SMEM_BYTES + 48 * 1024);
+    });
     if (e != cudaSuccess) return e;
-    if (dev < 64 && !configured[dev]) {
-        e = cudaFuncSetAttribute(gru_mma_kernel<FMT, NT, HALF, false, DEFER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 C::SMEM_BYTES + 48 * 1024);
-        if (e != cudaSuccess) return e;
-        configured[dev] = true;
-    }
     constexpr int SC = HALF ? 4 : C::S;
     const long long grid = (a.B + SC - 1) / SC;
     // DiffDelRNN: keep the last D + CH samples of pre_d per stream on chip if they fit (<= 48 KB of ring per CTA, so that
@@ -560,19 +633,19 @@ cudaError_t launch_mma_one(const GruArgs& a, cudaStream_t st)
             smem_bytes += (int)(rl * SC * 4);
         }
     }
-    gru_mma_kernel<FMT, NT, HALF, false, DEFER><<<(unsigned)grid, 128, smem_bytes, st>>>(b);
+    gru_mma_kernel<FMT, NT, HALF, false, DEFER, SPLIT><<<(unsigned)grid, 128, smem_bytes, st>>>(b);
     ++g_launches;
     return cudaGetLastError();
 }
 
-template <int FMT>
+template <int FMT, bool SPLIT = false>
 cudaError_t launch_mma_rt_fmt(const GruArgs& a, cudaStream_t st)
 {
-    using C = MmaCfg<FMT, 1>;
-    cudaError_t e = cudaFuncSetAttribute(gru_mma_kernel<FMT, 1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         C::SMEM_BYTES);
+    using C = MmaCfg<FMT, 1, SPLIT>;
+    cudaError_t e = cudaFuncSetAttribute(gru_mma_kernel<FMT, 1, true, true, !SPLIT, SPLIT>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    gru_mma_kernel<FMT, 1, true, true><<<1, 128, C::SMEM_BYTES, st>>>(a);
+    gru_mma_kernel<FMT, 1, true, true, !SPLIT, SPLIT><<<1, 128, C::SMEM_BYTES, st>>>(a);
     ++g_launches;
     return cudaGetLastError();
 }
@@ -581,17 +654,21 @@ template <int FMT>
 cudaError_t launch_mma_fmt(const GruArgs& a, int nt, cudaStream_t st)
 {
     if (nt >= 2) return launch_mma_one<FMT, 2, false>(a, st);
-    if (nt == 0) return launch_mma_one<FMT, 1, true>(a, st);
+    if (nt <= 0) return launch_mma_one<FMT, 1, true>(a, st);
     return launch_mma_one<FMT, 1, false>(a, st);
 }
 
 }  // namespace
 
-// fmt: FMT_F16 / FMT_BF16 / FMT_TF32.  n_tiles: 8-stream tiles per CTA (1 or 2); 0 = four streams per CTA (HALF).
+// fmt: FMT_F16 / FMT_BF16 / FMT_TF32 / FMT_F16X3 (strict: f16 hi/lo pairs, three MMAs per product).  n_tiles: 8-stream
+// tiles per CTA (1 or 2; the strict form has 1); 0 = four streams per CTA (HALF).
 cudaError_t launch_gru_mma(const GruArgs& a, int fmt, int n_tiles, cudaStream_t st)
 {
     if (a.B <= 0 || a.T <= 0) return cudaSuccess;
     switch (fmt) {
+        case FMT_F16X3:
+            return n_tiles <= 0 ? launch_mma_one<FMT_F16, 1, true, false, true>(a, st)
+                                : launch_mma_one<FMT_F16, 1, false, false, true>(a, st);
         case FMT_TF32: return launch_mma_fmt<FMT_TF32>(a, n_tiles, st);
         case FMT_BF16: return launch_mma_fmt<FMT_BF16>(a, n_tiles, st);
         default: return launch_mma_fmt<FMT_F16>(a, n_tiles, st);
@@ -603,6 +680,7 @@ cudaError_t launch_gru_mma_rt(const GruArgs& a, int fmt, cudaStream_t st)
 {
     if (a.B <= 0 || a.B > RT_MAXSTREAMS || a.T <= 0 || a.T > RT_MAXBLK || !a.rt || a.d) return cudaErrorInvalidValue;
     switch (fmt) {
+        case FMT_F16X3: return launch_mma_rt_fmt<FMT_F16, true>(a, st);
         case FMT_TF32: return launch_mma_rt_fmt<FMT_TF32>(a, st);
         case FMT_BF16: return launch_mma_rt_fmt<FMT_BF16>(a, st);
         default: return launch_mma_rt_fmt<FMT_F16>(a, st);

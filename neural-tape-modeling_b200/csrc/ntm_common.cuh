@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 namespace ntm {
 
 constexpr int H64 = 64;      // hidden size all shipped checkpoints use
@@ -17,12 +19,20 @@ struct BlobLayout {
     static constexpr int W_OUT = B_HH + G192;         // 64
     static constexpr int B_OUT = W_OUT + H64;         // 1 (0 when the head has no bias)
     static constexpr int FP32_END = B_OUT + 4;
-    // tensor-core A-operand images (gru_tc.cu): 3 gate tiles x 128 rows x 80 k (64 + the input/bias augmentation) of
-    // 2-byte elements, row-major; one image per operand format
+    // B-operand images of the stream-major tcgen05 kernel (gru_tcs.cu, pack_tc_images): row n = gate * 64 + unit (192
+    // rows), k contiguous, rows pre-scaled by -log2 e (r, z) / 2 log2 e (n); one image per operand format:
+    //   f16, bf16   80 k of 2 bytes: W_hh row | the K augmentation carrying W_i x + b (see gru_tcs.cu)
+    //   f16x3       192 k of 2 bytes (strict): G W_hi | G W_hi / 2^8 | (G W)_lo, G = TcsConsts::gain
+    //   tf32        64 k of 4 bytes
     static constexpr int IMG_F16 = FP32_END;
-    static constexpr int IMG_BF16 = IMG_F16 + 3 * 128 * 80 / 2;
-    static constexpr int TOTAL = IMG_BF16 + 3 * 128 * 80 / 2;
-    __host__ __device__ static constexpr int tc_image(int fmt) { return fmt == 1 ? IMG_BF16 : IMG_F16; }
+    static constexpr int IMG_BF16 = IMG_F16 + 192 * 80 / 2;
+    static constexpr int IMG_F16X3 = IMG_BF16 + 192 * 80 / 2;
+    static constexpr int IMG_TF32 = IMG_F16X3 + 192 * 192 / 2;
+    static constexpr int TOTAL = IMG_TF32 + 192 * 64;
+    __host__ __device__ static constexpr int tc_image(int fmt)
+    {
+        return fmt == 1 ? IMG_BF16 : fmt == 2 ? IMG_TF32 : fmt == 3 ? IMG_F16X3 : IMG_F16;
+    }
 };
 static_assert(BlobLayout::FP32_END % 4 == 0, "tensor-core images must stay 16-byte aligned");
 
@@ -58,23 +68,27 @@ struct GruArgs {
     int skip;
     int ring_len;                   // mma.sync kernel, DiffDelRNN: samples of pre_d kept per stream in shared memory
                                     // (power of two >= D + chunk; 0: read the delay taps back through L2)
+    int sm_count;                   // SMs of the handle's device (host-side dispatch only)
     RtMailbox* rt;                  // real-time server form only (x, y point into it)
     unsigned long long rt_idle_ns;  // the server leaves after this long without a block
 };
 
 // Warp-uniform per-unit constants of the stream-major tcgen05 kernel (gru_tcs.cu); passed as a kernel parameter so
-// that they are constant-bank operands.  Scaled like the n-gate rows (2 log2 e).
+// that they are constant-bank operands.  Scaled like the gate rows they belong to (-log2 e for r, z; 2 log2 e for n).
 struct TcsConsts {
     float cn_w[64];   // W_in
     float cn_b[64];   // b_in
     float wo[64];     // output head
+    // operand formats without the K augmentation (strict f16x3, tf32): input projection and biases are added in fp32
+    float cr_w[64], cr_b[64];   // W_ir, b_ir + b_hr
+    float cz_w[64], cz_b[64];   // W_iz, b_iz + b_hz
+    float ch_b[64];             // b_hn
     float bo;
+    float gain_inv;             // strict form: the weight image is scaled by the power of two `gain` (f16 range), 1 / gain
 };
 
 // per-TU launchers -------------------------------------------------------------------------------
 cudaError_t launch_gru_fp32(const GruArgs& a, int sm_count, int tune_s, int tune_ks, int fast_act, cudaStream_t st);
-cudaError_t launch_gru_tc(const GruArgs& a, int fmt, int sm_count, int tune_n, int tune_g, cudaStream_t st);
-cudaError_t launch_gru_mma8(const GruArgs& a, int fmt, cudaStream_t st);     // 8 warps x 8 streams per CTA (gru_mma8.cu)
 cudaError_t launch_gru_tcs(const GruArgs& a, const TcsConsts& kc, int fmt, int sm_count, int tiles, int var, cudaStream_t st);
 void fill_tcs_consts(const float* blob_host, TcsConsts* kc);
 cudaError_t launch_gru_mma(const GruArgs& a, int fmt, int n_tiles, cudaStream_t st);
@@ -86,10 +100,31 @@ cudaError_t launch_delay(const float* x, long long ldx, const float* d, long lon
 cudaError_t launch_delay_check(const float* d, long long ldd, long long B, long long T, long long D, int* flag_dev,
                                cudaStream_t st);
 
+// per_row == 0: sums[2] over all B x T samples; per_row != 0: sums[B][2], row b over samples [first[b], first[b] + count[b])
+// (first / count: device arrays or nullptr = 0 / T)
 cudaError_t launch_esr(const float* out, long long ldo, const float* tgt, long long ldt, long long B, long long T,
-                       int dc_pre, double* sums, int sm_count, cudaStream_t st);
+                       int dc_pre, double* sums, int sm_count, cudaStream_t st, const long long* first = nullptr,
+                       const long long* count = nullptr, int per_row = 0);
 
-extern unsigned long long g_launches;   // engine kernels launched by this process (ntm_query)
+extern std::atomic<unsigned long long> g_launches;   // engine kernels launched by this process (ntm_query)
+
+// One-time per-device kernel configuration (cudaFuncSetAttribute) without mutable statics that race when several host
+// threads drive several devices: a bit per device, set after the first successful configuration (idempotent if two
+// threads race to it).
+struct OncePerDevice {
+    std::atomic<unsigned long long> done{0};
+    template <class F>
+    cudaError_t run(F configure)
+    {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        if (dev < 64 && ((done.load(std::memory_order_acquire) >> dev) & 1ull)) return cudaSuccess;
+        e = configure();
+        if (e == cudaSuccess && dev < 64) done.fetch_or(1ull << dev, std::memory_order_release);
+        return e;
+    }
+};
 
 // ------------------------------------------------------------------------------------------------
 // Fractional delay read shared by the fused and the stand-alone kernels.

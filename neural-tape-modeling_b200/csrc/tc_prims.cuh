@@ -111,6 +111,7 @@ __host__ __device__ constexpr uint32_t instr_desc(int fmt, int M, int N)
            ((uint32_t)(M >> 4) << 24);
 }
 constexpr int FMT_F16 = 0, FMT_BF16 = 1, FMT_TF32 = 2;
+constexpr int FMT_F16X3 = 3;     // launcher-level selector of the strict split form (f16 hi/lo pairs); not an MMA kind
 
 // byte offset of element (row, k) inside a K-major no-swizzle operand tile; ELT = bytes per element
 template <int ELT>

@@ -192,18 +192,30 @@ class BatchedEvaluator:
                         y = self._apply_delay(d, y)
                 yh = y.cpu() if out_dir is not None else None
                 ph = pre.cpu() if out_dir is not None and write_pre_d and pre is not None else None
+                # targets of the whole group, padded like the inputs; every example is scored over its own window
+                # [init_len, min(len(target), len(input))) in ONE launch per loss (ESRLoss.per_example)
+                scored = [i for i, ex in enumerate(group) if "target_file" in ex]
+                group_losses = {}
+                if scored:
+                    th = torch.zeros((B, 1, Tmax), dtype=torch.float32, pin_memory=True)
+                    counts = torch.zeros(B, dtype=torch.int64)
+                    for i in scored:
+                        t, _ = self._load(group[i], "target_file")
+                        n = min(len(t), lens[i])
+                        th[i, 0, :n] = torch.from_numpy(np.array(t[:n]))
+                        counts[i] = max(n - init_len, 0)
+                    td = th.to(dev, non_blocking=True)
+                    first = torch.full((B,), int(init_len), dtype=torch.int64)
+                    for key, fn in self.losses.items():
+                        group_losses[key] = fn.per_example(y, td, first, counts).cpu()
                 for i, ex in enumerate(group):
                     name = os.path.basename(ex["input_file"])
                     off = ex.get("offset", 0)
                     stem, ext = os.path.splitext(name)
                     res = {"input_name": f"{stem}_[{off}:{off + lens[i]}]{ext}", "frames": lens[i], "fs": loaded[i][1]}
                     if "target_file" in ex:
-                        t, _ = self._load(ex, "target_file")
-                        n = min(len(t), lens[i])
-                        td = torch.from_numpy(t[:n]).to(dev).reshape(1, 1, n)
-                        od = y[i:i + 1, :, :n]
-                        for key, fn in self.losses.items():
-                            res[key] = float(fn(od[:, :, init_len:], td[:, :, init_len:]))
+                        for key in self.losses:
+                            res[key] = float(group_losses[key][i])
                     if out_dir is not None:
                         os.makedirs(out_dir, exist_ok=True)
                         res["output_file"] = os.path.join(out_dir, f"{stem}_[{off}:{off + lens[i]}]_pred.wav")

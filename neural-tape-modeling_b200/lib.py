@@ -10,10 +10,13 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("NTM_B200_LIB") or os.path.join(PKG, "libntm_b200.so")
 
 MODE_FP32, MODE_TF32, MODE_BF16, MODE_TF32X3, MODE_F16 = 0, 1, 2, 3, 4
-MODES = {"fp32": MODE_FP32, "tf32": MODE_TF32, "bf16": MODE_BF16, "tf32x3": MODE_TF32X3, "f16": MODE_F16}
+MODE_F16X3 = MODE_TF32X3
+# "f16x3" (aliases "strict", "tf32x3"): fp32-grade result on tensor cores, see include/ntm_b200.h NTM_MODE_F16X3
+MODES = {"fp32": MODE_FP32, "tf32": MODE_TF32, "bf16": MODE_BF16, "f16x3": MODE_F16X3, "strict": MODE_F16X3,
+         "tf32x3": MODE_F16X3, "f16": MODE_F16}
 Q_VERSION, Q_DEVICE_COUNT, Q_SM_COUNT, Q_MODE_MASK, Q_KERNEL_LAUNCHES, Q_LAST_KERNEL = 0, 1, 2, 3, 4, 5
-KERNEL_NAMES = {0: "gru_fp32_kernel (CUDA-core FFMA)", 1: "gru_mma_kernel (warp-level mma.sync)", 2: "gru_tc_kernel (tcgen05 + TMEM, weight-stationary)",
-                3: "gru_tcs_kernel (tcgen05 + TMEM, stream-major)", 4: "gru_mma8_kernel (warp-level mma.sync, 8 warps x 8 streams)"}
+KERNEL_NAMES = {0: "gru_fp32_kernel (CUDA-core FFMA)", 1: "gru_mma_kernel (warp-level mma.sync)",
+                3: "gru_tcs_kernel (tcgen05 + TMEM, stream-major)"}
 E_DELAY = -5
 E_CLOSED = -7
 
@@ -28,6 +31,11 @@ SIGNATURES = {
     "ntm_last_cuda_error": (_int, []),
     "ntm_gru_prepare": (_int, [_vp] * 6 + [_int, _int, ctypes.POINTER(_vp)]),
     "ntm_destroy": (None, [_vp]),
+    "ntm_retain": (_int, [_vp]),
+    "ntm_release": (None, [_vp]),
+    "ntm_handle_set_tuning": (_int, [_vp, _int, _int]),
+    "ntm_handle_last_kernel": (_int, [_vp]),
+    "ntm_esr_sums_rows": (_int, [_vp, _i64, _vp, _i64, _i64, _i64, _vp, _vp, _int, _vp, _int, _vp]),
     "ntm_gru_forward": (_int, [_vp, _int, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _i64, _int, _vp]),
     "ntm_diffdel_forward": (_int, [_vp, _int, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp,
                                    _i64, _i64, _i64, _int, _int, _vp]),
@@ -59,6 +67,24 @@ def load():
             fn.argtypes = args
         _lib = lib
     return _lib
+
+
+TORCH_LIB_PATH = os.environ.get("NTM_B200_TORCH_LIB") or os.path.join(PKG, "ntm_b200_torch.so")
+_ops = None
+
+
+def ops():
+    """torch.ops.ntm -- the PyTorch C++ extension (csrc/torch_binding.cpp) over the same C ABI.  No fallback either."""
+    global _ops
+    if _ops is None:
+        import torch
+        if not os.path.exists(TORCH_LIB_PATH):
+            raise RuntimeError(f"{TORCH_LIB_PATH} is missing: build it first (python neural-tape-modeling_b200/build.py); "
+                               "ntm_b200 has no fallback path")
+        load()                                   # the extension resolves libntm_b200.so next to itself ($ORIGIN rpath)
+        torch.ops.load_library(TORCH_LIB_PATH)
+        _ops = torch.ops.ntm
+    return _ops
 
 
 def check(rc):

@@ -42,15 +42,31 @@ class ESRLoss(torch.nn.Module):
         if t.device != o.device:
             raise RuntimeError("ntm_b200: output and target live on different devices")
         B, T = o.shape
-        sums = torch.empty(2, dtype=torch.float64, device=o.device)
-        ldo = o.stride(0) if B > 1 else max(T, 1)
-        ldt = t.stride(0) if B > 1 else max(T, 1)
-        with torch.cuda.device(o.device):
-            stream = torch.cuda.current_stream(o.device).cuda_stream
-            lib.check(lib.load().ntm_esr_sums(o.data_ptr(), ldo, t.data_ptr(), ldt, B, T, int(self.dc_pre),
-                                              sums.data_ptr(), o.device.index, stream))
+        sums = lib.ops().esr_sums(o, t, self.dc_pre)
         n = max(B * T, 1)
         return ((sums[0] / n) / (sums[1] / n + self.epsilon)).float()
+
+    def per_example(self, output, target, first=None, count=None):
+        """One loss per row of a (ragged) batch in ONE launch: row b is scored over its own window of samples
+        [first[b], first[b] + count[b]) -- what the reference computes with batch size 1, file by file, after cutting
+        INIT_LEN (code/test-model.py:367-370,385-397).  first / count: int64 tensors of B values or None (0 / T).
+        -> float32 tensor of B losses (no host synchronisation)."""
+        if not output.is_cuda or not target.is_cuda:
+            raise RuntimeError("ntm_b200: the engine has no CPU path; move output/target to a CUDA device")
+        if output.shape != target.shape:
+            raise RuntimeError(f"ntm_b200: output {tuple(output.shape)} and target {tuple(target.shape)} differ")
+        o, t = self._rows(output, "output"), self._rows(target, "target")
+        B, T = o.shape
+        dev = o.device
+        if first is not None:
+            first = torch.as_tensor(first, dtype=torch.int64).to(dev).contiguous()
+        if count is not None:
+            count = torch.as_tensor(count, dtype=torch.int64).to(dev).contiguous()
+        sums = lib.ops().esr_sums_rows(o, t, first, count, self.dc_pre)
+        f0 = torch.zeros(B, dtype=torch.int64, device=dev) if first is None else first.clamp(0, T)
+        n = (T - f0) if count is None else torch.minimum(count.clamp(min=0), T - f0)
+        n = n.clamp(min=1).to(torch.float64)
+        return ((sums[:, 0] / n) / (sums[:, 1] / n + self.epsilon)).float()
 
 
 class DCPreESR(ESRLoss):

@@ -6,10 +6,12 @@
 
 Same constructor arguments, attribute names, state_dict keys and method signatures, so
 `from model import RNN, DiffDelRNN, TimeVaryingDelayLine` in code/test-model.py:29 can point here.
-All arithmetic runs in libntm_b200.so (hand-written sm_100a CUDA) through the C ABI of
-include/ntm_b200.h; torch only owns the memory and the stream.  There is no CPU path and no
-torch.nn.GRU fallback: tensors must live on a CUDA device, otherwise a RuntimeError is raised.
-Training (train_epoch / validate, code/model.py:90-216, :426-616) is out of scope.
+All arithmetic runs in libntm_b200.so (hand-written sm_100a CUDA) behind the C ABI of include/ntm_b200.h, reached
+through the PyTorch C++ extension ntm_b200_torch.so (torch.ops.ntm.*, csrc/torch_binding.cpp: CUDAGuard on the
+input's device, PyTorch's current stream, TORCH_CHECK on a non-zero return code); torch only owns the memory and the
+stream.  The host-buffer pipeline (predict_host) and the resident real-time server bind the same C ABI with ctypes.
+There is no CPU path and no torch.nn.GRU fallback: tensors must live on a CUDA device, otherwise a RuntimeError is
+raised.  Training (train_epoch / validate, code/model.py:90-216, :426-616) is out of scope.
 
 Deliberate differences from the reference:
   * the device is the input tensor's device, not the global "cuda" (needed to shard streams over 8 GPUs);
@@ -63,35 +65,53 @@ def _as_rows(t, name):
     return t, B, T, ld
 
 
-def _version(p):
-    try:
-        return p._version
-    except RuntimeError:            # inference tensors carry no version counter
-        return -1
-
-
 class _Engine:
-    """Owns the packed-parameter handle of one module on one device; re-prepared when parameters change."""
+    """Owns the packed-parameter handle of one module on one device; re-prepared when parameters change.
+
+    Change detection: data_ptr + the autograd version counter of every parameter.  Inference tensors (modules built or
+    moved under torch.inference_mode()) carry no version counter: for them an in-place edit of a parameter is not seen --
+    call `module.refresh_parameters()` after one (load_state_dict / .to() / .float() always re-pack)."""
 
     def __init__(self):
-        self.handle = None
-        self.key = None
+        self.handle = None          # int (a Handle* of the C ABI)
+        self.generation = 0         # bumped whenever the handle is released: live BlockStreams re-resolve theirs
+        self._params = ()
+        self._ptrs = ()
+        self._versions = None       # None: inference tensors, no version counters
+        self._device = None
         self._finalizer = None
 
+    def _stale(self, params, device):
+        if self.handle is None or device != self._device:
+            return True
+        for p, q, ptr in zip(params, self._params, self._ptrs):
+            if p is not q or (p is not None and p.data_ptr() != ptr):
+                return True
+        if self._versions is not None:
+            for p, v in zip(params, self._versions):
+                if p is not None and p._version != v:
+                    return True
+        return False
+
     def get(self, gru, head, device):
-        params = [gru.weight_ih_l0, gru.weight_hh_l0, gru.bias_ih_l0, gru.bias_hh_l0, head.weight, head.bias]
-        key = (device.index,) + tuple((p.data_ptr(), _version(p)) if p is not None else None for p in params)
-        if key != self.key:
+        params = (gru.weight_ih_l0, gru.weight_hh_l0, gru.bias_ih_l0, gru.bias_hh_l0, head.weight, head.bias)
+        if self._stale(params, device):
             self.release()
-            host = [None if p is None else p.detach().to("cpu", torch.float32).contiguous() for p in params]
-            H = host[1].shape[1]
-            if host[0].shape[1] != 1 or head.weight.shape[0] != 1:
+            H = params[1].shape[1]
+            if params[0].shape[1] != 1 or head.weight.shape[0] != 1:
                 raise RuntimeError("ntm_b200: only input_size=1, output_size=1 models are supported")
-            handle = ctypes.c_void_p()
-            rc = _lib.load().ntm_gru_prepare(*[_ptr(t) for t in host], H, device.index, ctypes.byref(handle))
-            _lib.check(rc)
-            self.handle, self.key = handle, key
-            self._finalizer = weakref.finalize(self, _lib.load().ntm_destroy, handle)
+            if H != 64:
+                raise RuntimeError(f"ntm_b200: only hidden_size=64 is built into the engine (all shipped checkpoints are "
+                                   f"GRU-HS[64]); this module has hidden_size={H}")
+            ops = _lib.ops()
+            handle = int(ops.prepare(*[p.detach() if p is not None else None for p in params], device.index))
+            self.handle, self._device = handle, device
+            self._params, self._ptrs = params, tuple(None if p is None else p.data_ptr() for p in params)
+            try:
+                self._versions = tuple(None if p is None else p._version for p in params)
+            except RuntimeError:            # inference tensors carry no version counter
+                self._versions = None
+            self._finalizer = weakref.finalize(self, ops.destroy, handle)
         return self.handle
 
     def __deepcopy__(self, memo):          # handles are per-object; a copied module re-prepares lazily
@@ -102,9 +122,10 @@ class _Engine:
 
     def release(self):
         if self._finalizer is not None:
-            self._finalizer()
+            self._finalizer()               # drops this module's reference (an open real-time stream keeps its own)
             self._finalizer = None
-        self.handle, self.key = None, None
+        self.handle, self._params, self._ptrs = None, (), ()
+        self.generation += 1
 
 
 class RNN(torch.nn.Module):
@@ -121,7 +142,13 @@ class RNN(torch.nn.Module):
         # parameter containers only (state_dict keys GRU.* / output.*); their forward() is never called
         self.GRU = torch.nn.GRU(input_size, hidden_size, batch_first=True)
         self.output = torch.nn.Linear(hidden_size, output_size, bias=self._head_bias)
-        self.mode = "fp32"          # "fp32" | "f16" | "tf32" | "bf16"  (include/ntm_b200.h NTM_MODE_*)
+        # "fp32" exact CUDA-core | "f16x3" (alias "strict") fp32-grade on tensor cores | "f16" | "tf32" | "bf16" rounded
+        # operands (include/ntm_b200.h NTM_MODE_*)
+        self.mode = "fp32"
+        # True: forward() writes into per-shape buffers it keeps (the returned tensor is overwritten by the next call of
+        # the same shape) -- no allocation per call, and the call sequence can be captured in a CUDA Graph
+        self.static_io = False
+        self._io = {}
         self._engine = _Engine()
         self.hidden = None
         # parameters are re-packed lazily whenever they may have changed
@@ -129,7 +156,12 @@ class RNN(torch.nn.Module):
 
     def _apply(self, fn, *args, **kwargs):      # .to() / .cuda() / .float() ...
         self._engine.release()
+        self._io = {}
         return super()._apply(fn, *args, **kwargs)
+
+    def refresh_parameters(self):
+        """Re-pack the parameters at the next call (needed only after an in-place edit of an inference-mode parameter)."""
+        self._engine.release()
 
     # -- state handling (code/model.py:50-56) ---------------------------------------------------
     def initialize_hidden(self):
@@ -163,17 +195,26 @@ class RNN(torch.nn.Module):
 
     def forward(self, x):
         """x (N_BATCHES, 1, N_SAMPLES) -> y of the same shape; carries self.hidden (code/model.py:67-88)."""
-        x, B, T, ldx = _as_rows(x, "x")
+        if not (x.dtype is torch.float32 and x.is_cuda and x.dim() == 3 and x.shape[1] == 1 and x.stride(2) == 1):
+            x = _as_rows(x, "x")[0]
         dev = x.device
         handle = self._handle(dev)
-        h_in = self._hidden_in(B, dev)
-        y = torch.empty((B, 1, T), dtype=torch.float32, device=dev)
-        h_out = torch.empty((1, B, self.hidden_size), dtype=torch.float32, device=dev)
-        # (no torch.cuda.device() context: the C ABI switches to the handle's device itself)
-        rc = _lib.load().ntm_gru_forward(handle, _lib.MODES[self.mode], _ptr(x), ldx, _ptr(y), max(T, 1),
-                                         _ptr(h_in), _ptr(h_out), B, T, int(bool(self.skip)), _stream(dev))
-        if rc:
-            _lib.check(rc)
+        B = x.shape[0]
+        h_in = self.hidden
+        if h_in is not None and not (h_in.shape[1] == B and h_in.device == dev and h_in.dtype is torch.float32
+                                     and h_in.is_contiguous()):
+            h_in = self._hidden_in(B, dev)
+        ops = _lib.ops()
+        if self.static_io:
+            key = (B, x.shape[2], dev)
+            buf = self._io.get(key)
+            if buf is None:
+                buf = self._io[key] = (torch.empty((B, 1, x.shape[2]), dtype=torch.float32, device=dev),
+                                       torch.empty((1, B, self.hidden_size), dtype=torch.float32, device=dev))
+            y, h_out = buf
+            ops.gru_forward_out(handle, _lib.MODES[self.mode], x, h_in, y, h_out, bool(self.skip))
+        else:
+            y, h_out = ops.gru_forward(handle, _lib.MODES[self.mode], x, h_in, bool(self.skip))
         self.hidden = h_out
         return y
 
@@ -232,7 +273,8 @@ class BlockStream:
         if dev.type != "cuda":
             raise RuntimeError("ntm_b200 has no CPU path; move the model to a CUDA device")
         self.model, self.B, self.T, self.device = model, int(n_streams), int(block_len), dev
-        self._handle = model._handle(dev)
+        self._handle = ctypes.c_void_p(model._handle(dev))
+        self._generation = model._engine.generation
         self._mode = _lib.MODES[model.mode]
         self._skip = int(bool(model.skip))
         h = model._hidden_in(self.B, dev)
@@ -250,6 +292,9 @@ class BlockStream:
                 or x.stride(2) != 1:
             raise RuntimeError(f"expected a float32 CUDA block of shape ({self.B}, 1, <= {self.T})")
         T = x.shape[2]
+        if self._generation != self.model._engine.generation:     # parameters were re-packed (load_state_dict, .to(), ...):
+            self._handle = ctypes.c_void_p(self.model._handle(self.device))      # the old handle is gone
+            self._generation = self.model._engine.generation
         y, yp = (self.y, self._yp) if out is None else (out, ctypes.c_void_p(out.data_ptr()))
         rc = self._fn(self._handle, self._mode, ctypes.c_void_p(x.data_ptr()), x.stride(0) if self.B > 1 else max(T, 1),
                       yp, y.stride(0) if self.B > 1 else max(T, 1), self._hp, self._hp, self.B, T, self._skip, self._st)
@@ -350,10 +395,15 @@ class TimeVaryingDelayLine(torch.nn.Module):
             buf = buf.to(device, torch.float32).contiguous()
         return buf
 
-    def _check(self, d, ldd, B, T, device):
-        if self.check_delay and T > 0:
-            _lib.check(_lib.load().ntm_delay_check(_ptr(d), ldd, B, T, int(self.max_delay), device.index,
-                                                   _stream(device)))
+    def _check(self, d):
+        """The reference's `assert self.max_delay >= torch.max(dt)` (code/model.py:283); NaN trips it too."""
+        if self.check_delay and d.shape[2] > 0:
+            if d.is_cuda:
+                ok = _lib.ops().delay_check(d, int(self.max_delay))
+            else:
+                ok = bool((d <= float(self.max_delay)).all())
+            if not ok:
+                raise AssertionError("delay exceeds max_delay (history length)")
 
     def forward(self, x, dt, warmup=False):
         """x, dt (N_BATCHES, 1, N_SAMPLES), dt in samples -> delayed x (code/model.py:269-320)."""
@@ -361,17 +411,9 @@ class TimeVaryingDelayLine(torch.nn.Module):
         dt, Bd, Td, ldd = _as_rows(dt.to(x.device), "dt")
         if (Bd, Td) != (B, T):
             raise RuntimeError(f"x {tuple(x.shape)} and dt {tuple(dt.shape)} must have the same shape")
-        dev = x.device
-        hist = self._history(B, dev)
-        D = int(self.max_delay)
-        with torch.cuda.device(dev):
-            self._check(dt, ldd, B, T, dev)
-            y = torch.empty((B, 1, T), dtype=torch.float32, device=dev)
-            hist_out = torch.empty((B, 1, D), dtype=torch.float32, device=dev)
-            rc = _lib.load().ntm_delay_forward(_ptr(x), ldx, _ptr(dt), ldd, _ptr(y), max(T, 1), _ptr(hist),
-                                               _ptr(hist_out), B, T, D, int(bool(warmup)), dev.index, _stream(dev))
-        _lib.check(rc)
-        self.buffer = hist_out
+        hist = self._history(B, x.device)
+        self._check(dt)
+        y, self.buffer = _lib.ops().delay_forward(x, dt, hist, bool(warmup))
         return y
 
     def detach_buffer(self):
@@ -423,20 +465,9 @@ class DiffDelRNN(RNN):
         handle = self._handle(dev)
         h_in = self._hidden_in(B, dev)
         hist = self.diffdel._history(B, dev)
-        D = int(self.diffdel.max_delay)
-        with torch.cuda.device(dev):
-            self.diffdel._check(d, ldd, B, T, dev)
-            y = torch.empty((B, 1, T), dtype=torch.float32, device=dev)
-            pre_d = torch.empty((B, 1, T), dtype=torch.float32, device=dev)
-            h_out = torch.empty((1, B, self.hidden_size), dtype=torch.float32, device=dev)
-            hist_out = torch.empty((B, 1, D), dtype=torch.float32, device=dev)
-            rc = _lib.load().ntm_diffdel_forward(handle, _lib.MODES[self.mode], _ptr(x), ldx, _ptr(d), ldd, _ptr(y),
-                                                 max(T, 1), _ptr(pre_d), max(T, 1), _ptr(h_in), _ptr(h_out),
-                                                 _ptr(hist), _ptr(hist_out), B, T, D, int(bool(warmup)),
-                                                 int(bool(self.skip)), _stream(dev))
-        _lib.check(rc)
-        self.hidden = h_out
-        self.diffdel.buffer = hist_out
+        self.diffdel._check(d)
+        y, pre_d, self.hidden, self.diffdel.buffer = _lib.ops().diffdel_forward(
+            handle, _lib.MODES[self.mode], x, d, h_in, hist, bool(warmup), bool(self.skip))
         return y, pre_d
 
     def predict(self, input, d_traj):
@@ -461,6 +492,7 @@ class DiffDelRNN(RNN):
         x = input.float().contiguous()
         d = d_traj.float().contiguous()
         B, T = x.shape[0], x.shape[2]
+        self.diffdel._check(d)                      # the assert forward() makes (code/model.py:283), on the host copy
         self.initialize_hidden(1, self.max_delay)
         self.warm_start()
         D = int(self.diffdel.max_delay)

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_query_and_strerror():
     L = lib.load()
-    assert L.ntm_query(lib.Q_VERSION) == 1
+    assert L.ntm_query(lib.Q_VERSION) == 2
     assert L.ntm_query(lib.Q_MODE_MASK) & 1
     assert L.ntm_query(12345) == -1
     assert L.ntm_strerror(0) == b"ok"

@@ -1,7 +1,8 @@
 """Parity of the CUDA path (through the C ABI) against the oracle and the committed golden vectors.
 
-Tolerances (BASELINE.json north_star): fp32 mode -- max-abs output error <= 1e-5 and |dESR| <= 1e-6 against the
-reference's fp32 torch.nn.GRU path on numerically stable inputs.  Where the reference's OWN fp32-vs-fp64 noise
+Tolerances (BASELINE.json north_star): fp32-class modes ("fp32": CUDA-core FFMA; "f16x3": the strict tensor-core mode, on the
+warp-level mma.sync kernel and on the stream-major tcgen05 kernel) -- max-abs output error <= 1e-5 and |dESR| <= 1e-6
+against the reference's fp32 torch.nn.GRU path on numerically stable inputs.  Where the reference's OWN fp32-vs-fp64 noise
 floor on a signal (stored with the fixture) is above 3e-6 the checkpoint is amplifying round-off there and the
 bound is widened by twice that floor; the delay line is bit-exact.
 """
@@ -19,8 +20,13 @@ DEV = "cuda:0"
 TOL = 1e-5
 
 
-def tol_for(floor):
-    return TOL if floor < 3e-6 else TOL + 2.0 * floor
+def tol_for(floor, vs_truth=True):
+    """Stable signal (the reference's own fp32-vs-fp64 floor < 3e-6): the north star's 1e-5.  Where the checkpoint amplifies
+    round-off (floor >= 3e-6) the engine is held to 1e-5 + 2 floors against the float64 ground truth, hence -- the fp32
+    reference itself being one floor away from that truth -- to 1e-5 + 3 floors against the fp32 reference."""
+    if floor < 3e-6:
+        return TOL
+    return TOL + (2.0 if vs_truth else 3.0) * floor
 
 
 def make_rnn(tag, skip=False, mode="fp32"):
@@ -49,10 +55,17 @@ def _auto_tuning():
 
 
 # ------------------------------------------------------------------------------------------- RNN
+# fp32-class (mode, kernel selector) pairs: (0, 0) automatic dispatch; (8, 3) / (4, 3) mma.sync with 8 / 4 streams per CTA;
+# (1, 4) / (2, 4) the stream-major tcgen05 kernel with one / two tiles per CTA
+STRICT_CLASS = [("fp32", (0, 0)), ("f16x3", (0, 0)), ("f16x3", (8, 3)), ("f16x3", (1, 4)), ("f16x3", (2, 4))]
+
+
+@pytest.mark.parametrize("mode,kernel", STRICT_CLASS)
 @pytest.mark.parametrize("tag", ["cfg1", "cfg2"])
-def test_rnn_predict_vs_golden(tag):
-    m = make_rnn(tag)
+def test_rnn_predict_vs_golden(tag, mode, kernel):
+    m = make_rnn(tag, mode=mode)
     g = load_golden(f"golden_{tag}")
+    lib.load().ntm_set_tuning(*kernel)
     with torch.inference_mode():
         m.initialize_hidden()
         m.warm_start()
@@ -62,7 +75,7 @@ def test_rnn_predict_vs_golden(tag):
             floor = float(g[f"floor_{sig}"])
             err = float(np.max(np.abs(y - g[f"y_{sig}"])))
             err64 = float(np.max(np.abs(y - g[f"y64_{sig}"])))
-            assert err <= tol_for(floor), (tag, sig, err, floor)
+            assert err <= tol_for(floor, vs_truth=False), (tag, sig, err, floor)
             assert err64 <= tol_for(floor), (tag, sig, err64, floor)
             t64 = g[f"y64_{sig}"].astype(np.float32)
             assert abs(c_oracle.esr(y, t64) - c_oracle.esr(g[f"y_{sig}"], t64)) <= 1e-6
@@ -247,9 +260,11 @@ def test_delay_line_assert_and_chunking():
 
 
 # ------------------------------------------------------------------------------------ DiffDelRNN
-def test_diffdel_predict_vs_golden():
+@pytest.mark.parametrize("mode,kernel", STRICT_CLASS)
+def test_diffdel_predict_vs_golden(mode, kernel):
     g = load_golden("golden_cfg3")
-    m = make_diffdel(int(g["max_delay"]))
+    m = make_diffdel(int(g["max_delay"]), mode=mode)
+    lib.load().ntm_set_tuning(*kernel)
     with torch.inference_mode():
         for sig in SIGNALS:
             x, d = dev(g[f"x_{sig}"]).reshape(1, 1, -1), dev(g[f"d_{sig}"]).reshape(1, 1, -1)
@@ -349,7 +364,7 @@ def _best12():
         yield i, str(g[f"kind{i}"]), {k[len(pre):]: torch.from_numpy(g[k]) for k in g.files if k.startswith(pre)}, g
 
 
-@pytest.mark.parametrize("mode", ["fp32", "f16"])
+@pytest.mark.parametrize("mode", ["fp32", "f16x3", "f16"])
 def test_all_12_shipped_best_checkpoints_vs_reference(mode):
     """`load_state_dict(strict=True)` of every weights/*_BEST/best.pth into the drop-in classes, warm-start known answer,
     and predict() on two signals against the REFERENCE's outputs (oracle/make_golden_best.py), packed as a batch of 3
@@ -372,7 +387,7 @@ def test_all_12_shipped_best_checkpoints_vs_reference(mode):
                 m.initialize_hidden(1, int(g["max_delay"]))
             m.warm_start()
             hw = m.hidden.cpu().numpy().reshape(-1)
-            assert np.max(np.abs(hw - g[f"h_warm{i}"])) < (5e-6 if mode == "fp32" else 5e-3), (i, mode)
+            assert np.max(np.abs(hw - g[f"h_warm{i}"])) < (5e-3 if mode == "f16" else 5e-6), (i, mode)
             for sig in g["signals"]:
                 floor = float(g[f"floor{i}_{sig}"])
                 x = dev(g[f"x_{sig}"]).reshape(1, 1, -1).expand(3, 1, -1).contiguous()
@@ -385,7 +400,7 @@ def test_all_12_shipped_best_checkpoints_vs_reference(mode):
                     outs = [(y.cpu().numpy(), g[f"y{i}_{sig}"]), (pre.cpu().numpy(), g[f"pre{i}_{sig}"])]
                 for got, want in outs:
                     assert np.array_equal(got[0], got[1]) and np.array_equal(got[0], got[2])
-                    if mode == "fp32":
+                    if mode != "f16":               # fp32-class: exact CUDA-core kernel and the strict tensor-core mode
                         err = float(np.max(np.abs(got[0, 0] - want)))
                         assert err <= tol_for(floor), (i, kind, sig, err, floor)
                     elif floor < 3e-6:

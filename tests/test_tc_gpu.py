@@ -1,4 +1,4 @@
-"""Tensor-core modes (tcgen05 kernel, csrc/gru_tc.cu) through the C ABI.
+"""Tensor-core modes (warp-level mma.sync kernel csrc/gru_mma.cu, stream-major tcgen05 kernel csrc/gru_tcs.cu) through the C ABI.
 
 Tolerance (BASELINE.json north_star): tf32/bf16-class MMA modes -- ESR of the output against the reference's fp32
 output <= 1e-4 on numerically stable inputs.  "f16" rounds the operands to an 11-bit significand exactly like tf32 and
@@ -41,19 +41,22 @@ def _auto_tuning():
 
 def test_mode_mask():
     mask = lib.query(lib.Q_MODE_MASK)
-    for m in ("fp32", "tf32", "bf16", "f16"):
+    for m in ("fp32", "tf32", "bf16", "f16", "f16x3"):
         assert mask >> lib.MODES[m] & 1
-    assert not mask >> lib.MODES["tf32x3"] & 1
-    m = make_rnn("cfg1", "tf32x3")
+    assert lib.MODES["strict"] == lib.MODES["tf32x3"] == lib.MODES["f16x3"]
+    m = make_rnn("cfg1", "f16")
     with pytest.raises(RuntimeError, match="unsupported"):
-        m.predict(torch.zeros(1, 1, 64, device=DEV))
+        x = torch.zeros(1, 1, 8, device=DEV)
+        lib.check(lib.load().ntm_gru_forward(m._handle(torch.device(DEV)), 17, x.data_ptr(), 8, x.data_ptr(), 8, None,
+                                             torch.zeros(64, device=DEV).data_ptr(), 1, 8, 0, None))
 
 
-# kernel selectors (ntm_set_tuning): (n, 1|2) weight-stationary tcgen05 kernel, (n, 3) mma.sync kernel with n = 4, 8, 16
-# streams per CTA,
-# (tiles, 4) stream-major tcgen05 kernel (f16/bf16 operands; tf32 falls through to mma.sync), (8, 5) the 8-warp mma.sync
-# form of gru_mma8.cu (a recorded experiment, never dispatched automatically)
-@pytest.mark.parametrize("kernel", [(32, 2), (8, 3), (4, 3), (1, 4), (2, 4), (8, 5)])
+# kernel selectors (ntm_set_tuning): (n, 3) mma.sync kernel with n = 4, 8, 16 streams per CTA, (tiles, 4) stream-major
+# tcgen05 kernel
+KERNELS = [(8, 3), (4, 3), (1, 4), (2, 4)]
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
 @pytest.mark.parametrize("mode", TC_MODES)
 @pytest.mark.parametrize("tag", ["cfg1", "cfg2"])
 def test_tc_predict_esr_vs_golden(tag, mode, kernel):
@@ -94,23 +97,22 @@ def test_tc_batch_vs_oracle_and_launch_shapes(mode):
         per_stream = ((y0.cpu() - yr) ** 2).sum(2) / ((yr ** 2).sum(2) + 1e-5)
         assert float(per_stream.max()) <= ESR_TOL
         assert abs(c_oracle.esr(y0.cpu().numpy(), yr.numpy())) <= ESR_TOL
-        # g = 1, 2: tcgen05 kernel (f16/bf16 operands; tf32 falls through to mma.sync) with n streams per group;
-        # g = 3: warp-level mma.sync kernel with n streams per CTA
+        # g = 3: warp-level mma.sync kernel with n streams per CTA; g = 4: stream-major tcgen05 kernel, n tiles per CTA
         fam = {}
-        for n, g in ((32, 1), (64, 1), (32, 2), (64, 2), (8, 3), (16, 3), (4, 3), (1, 4), (2, 4)):
+        for n, g in ((8, 3), (16, 3), (4, 3), (1, 4), (2, 4)):
             lib.load().ntm_set_tuning(n, g)
             y = m.predict(x)
             per_stream = ((y.cpu() - yr) ** 2).sum(2) / ((yr ** 2).sum(2) + 1e-5)
             assert float(per_stream.max()) <= ESR_TOL, (n, g)
-            # same kernel family and form: same arithmetic (the 4-streams-per-CTA form uses its own reciprocals)
-            first = fam.setdefault((g, n == 4) if g >= 3 or mode == "tf32" else 1, y)
+            # same kernel family and form: same arithmetic (the 4-streams-per-CTA forms use their own reciprocals)
+            first = fam.setdefault((g, n == 4), y)
             assert float((y - first).abs().max()) <= 1e-6, (n, g)      # same kernel family: same arithmetic
             for b in (0, 31, 76):
                 assert float((m.predict(x[b:b + 1]) - y[b:b + 1]).abs().max()) <= 1e-6
 
 
-@pytest.mark.parametrize("kernel", [(0, 0), (32, 2), (64, 1), (8, 3), (4, 3), (1, 4), (2, 4), (8, 5)])
-@pytest.mark.parametrize("mode", TC_MODES)
+@pytest.mark.parametrize("kernel", [(0, 0)] + KERNELS)
+@pytest.mark.parametrize("mode", TC_MODES + ("f16x3",))
 def test_tc_segmentation_state_and_skip(mode, kernel):
     lib.load().ntm_set_tuning(*kernel)
     m = make_rnn("cfg1", mode)
@@ -132,7 +134,7 @@ def test_tc_segmentation_state_and_skip(mode, kernel):
         assert torch.equal(m.predict(view), m.predict(view.contiguous()))
 
 
-@pytest.mark.parametrize("kernel", [(32, 2), (8, 3), (4, 3)])
+@pytest.mark.parametrize("kernel", [(8, 3), (4, 3), (1, 4), (2, 4)])
 @pytest.mark.parametrize("mode", TC_MODES)
 def test_tc_diffdel(mode, kernel):
     lib.load().ntm_set_tuning(*kernel)
@@ -243,7 +245,7 @@ def test_stream_major_dynamic_schedule_is_exact():
         for tiles, B, T in ((2, sms * 256 + 300, 700), (1, sms * 128 + 1000, 900)):
             x = signals.stream_batch_device(B, T, DEV, dur=10.0).reshape(B, 1, T)
             outs = []
-            for var in (31, 63):                                  # default variant: dynamic, static
+            for var in (7, 39):                                   # default variant: dynamic, static (bit 32)
                 lib.load().ntm_set_tuning(tiles + 4 * (var + 1), 4)
                 m.hidden = hw.expand(1, B, 64).contiguous()
                 outs.append((m(x), m.hidden.clone()))
