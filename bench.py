@@ -136,21 +136,23 @@ def reference_runner():
     return (lambda x: net.predict(x)[0]), "port", "oracle/ref_torch.py (torch.nn.GRU + Linear restated; baseline/_ref not staged)"
 
 
-REF_SEGMENTS = 2          # 2048-sample segments per reference step (both the --impl reference arm and cpu_baseline)
+REF_SEGMENTS = int(os.environ.get("NTM_REF_SEGMENTS", "2"))   # 2048-sample segments per reference step (the --impl reference arm and cpu_baseline)
 
 
 def cpu_baseline(B, seg_count, threads):
-    """The reference on the host cores over a bounded sample: `seg_count` 2048-sample segments of B streams."""
-    from ntm_b200 import signals
-    torch.set_num_threads(threads)
-    run, kind, desc = reference_runner()
-    T = 2048 * seg_count
-    x = torch.from_numpy(signals.stream_batch(B, T, dur=60.0)).reshape(B, 1, T)
-    run(x[:, :, :2048])                                          # warm-up of the MKL/oneDNN paths
-    t0 = time.perf_counter()
-    run(x)
-    dt = time.perf_counter() - t0
-    return B * T / dt, kind, f"{B} streams x {T} samples ({seg_count} x 2048-sample segments); {desc}; torch {torch.__version__}"
+    """The reference on the host cores over a bounded sample: `seg_count` 2048-sample segments of B streams.  Runs in a child
+    process that does not see the GPUs: the reference's RNN pins its state to "cuda" whenever torch sees one
+    (code/model.py:61,223), and this leg is its CPU path."""
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="", NTM_REF_SEGMENTS=str(seg_count))
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                        "--streams", str(B)], env=env, capture_output=True, text=True, timeout=900)
+    if r.returncode != 0:
+        raise RuntimeError("cpu_baseline child failed:\n" + r.stderr[-2000:])
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    c = line["cpu_baseline"]
+    return c["value"], c["kind"], c["sample"] + f"; torch {torch.__version__}"
 
 
 def run_reference(args, rank):

@@ -195,3 +195,55 @@ def test_evaluator_trajectory_sources_and_errors(tmp_path):
     from ntm_b200 import DiffDelRNN, TimeVaryingDelayLine
     with pytest.raises(ValueError):                       # ADD_DELAY is a plain-GRU mode (code/test-model.py:354)
         driver.BatchedEvaluator(DiffDelRNN(1, 64, 1, False, max_delay=8), delay=TimeVaryingDelayLine(max_delay=8))
+
+
+# ---- the native RIFF/WAVE reader against reference-held audio -------------------------
+REF_RESULTS = "/root/reference/results"
+
+
+def _scipy_float(path):
+    import warnings
+    import scipy.io.wavfile as wavfile
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        fs, a = wavfile.read(path)
+    a = a.reshape(len(a), -1).T
+    if a.dtype == np.int16:
+        a = a.astype(np.float32) / 32768.0
+    return fs, np.ascontiguousarray(a.astype(np.float32))
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_RESULTS), reason="the reference tree (results/**.wav) only exists in the build container")
+def test_read_wav_equals_scipy_on_every_reference_held_wav():
+    """All .wav files the reference ships (results/**: 125 int16 + 20 float32 files with extra RIFF chunks), whole-file and
+    segment reads (`frame_offset` / `num_frames` of code/dataset.py:362-365), against scipy.io.wavfile."""
+    import glob
+    files = sorted(glob.glob(os.path.join(REF_RESULTS, "**", "*.wav"), recursive=True))
+    assert len(files) >= 100
+    kinds = set()
+    for i, path in enumerate(files):
+        fs, want = _scipy_float(path)
+        info = driver.wav_info(path)
+        kinds.add((info["format"], info["bits"]))
+        assert (info["fs"], info["channels"], info["frames"]) == (fs, want.shape[0], want.shape[1]), path
+        if i % 6 == 0:                                   # whole file (every file would take ~20 s of the CPU suite)
+            got, fs2 = driver.read_wav(path)
+            assert fs2 == fs and np.array_equal(got, want), path
+        off, n = 1000 + 37 * i, 4096
+        seg, _ = driver.read_wav(path, off, n)
+        assert np.array_equal(seg, want[:, off:off + n]), path
+        tail, _ = driver.read_wav(path, want.shape[1] - 100, 4096)          # clipped at the end of the file
+        assert np.array_equal(tail, want[:, -100:]), path
+    assert kinds == {(1, 16), (3, 32)}
+
+
+@pytest.mark.parametrize("name", ["ref_int16_head.wav", "ref_float32_head.wav"])
+def test_read_wav_on_committed_reference_excerpts(name):
+    """The first 2048 frames of one int16 and one float32 reference-held file (tests/golden/, cut by
+    oracle/make_golden_wav.py with the original headers and extra chunks kept): runs wherever the repository is."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name)
+    fs, want = _scipy_float(path)
+    got, fs2 = driver.read_wav(path)
+    assert fs2 == fs == 44100 and got.shape == (1, 2048) and np.array_equal(got, want)
+    seg, _ = driver.read_wav(path, 100, 50)
+    assert np.array_equal(seg, want[:, 100:150])
