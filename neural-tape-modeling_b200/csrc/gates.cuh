@@ -77,6 +77,14 @@ __device__ __forceinline__ void gates_blend2(float z0, float dn0, float h0, floa
     hn1 = fmaf(z1, h1 - n1, n1);
 }
 
+// The single-pair blend with everything that does not depend on the n gate's reciprocal moved in front of it:
+//     h' = (1 - z) (1 - 2 q) + z h = [z h + 1 - z] + [-2 (1 - z)] q,   q = 1 / dn
+// -- ONE dependent FMA behind the last MUFU of the step instead of three.
+__device__ __forceinline__ float gates_blend1_late(float z, float dn, float h)
+{
+    const float a = fmaf(z, h - 1.0f, 1.0f), b = fmaf(2.0f, z, -2.0f);
+    return fmaf(b, rcp_approx(dn), a);
+}
 // 2^x on the FMA/ALU pipes (no MUFU): round-to-nearest split x = i + f, f in [-0.5, 0.5], degree-5 minimax polynomial
 // (max relative error 2.4e-7 in fp32 Horner form = the accuracy class of ex2.approx), exponent inserted by an integer
 // add.  x must be <= 127 on entry (callers clamp to EX2_CLAMP); clamped below at -125 (result ~2^-125 instead of 0).
