@@ -302,7 +302,7 @@ def main():
         # ---- end to end: pinned host in -> engine pipeline -> pinned host out -------------------------
         import psutil
         avail = psutil.virtual_memory().available
-        need = 2 * B * T * 4 * max(1, min(world, 8))          # pinned x and y of every rank on this host
+        need = 3 * B * T * 4 * max(1, min(world, 8))          # pinned x and y (float32, then binary16) of every rank on this host
         T_e = T if need < 0.5 * avail else max(FS, int(0.25 * avail / (8 * B * max(1, world))) // FS * FS)
         numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 else None
         xh = torch.empty((B, 1, T_e), dtype=torch.float32, pin_memory=True)
@@ -317,7 +317,22 @@ def main():
         e2e_s = time.perf_counter() - t0
         e2e_value = sharding.aggregate_rate(B * T_e * args.e2e_steps, world, sharding.max_over_ranks(e2e_s, dev, dist))
         e2e_ok = bool(torch.isfinite(yh[:, :, ::4801]).all())
-        del xh, yh
+        # the same call with the opt-in 16-bit host transport (ntm_gru_predict_host_f16): binary16 samples over the host link
+        xh16 = torch.empty((B, 1, T_e), dtype=torch.float16, pin_memory=True)
+        xh16.copy_(x[:, :, :T_e])
+        yh16 = torch.empty((B, 1, T_e), dtype=torch.float16, pin_memory=True)
+        model.predict_host(xh16, out=yh16)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            model.predict_host(xh16, out=yh16)
+        torch.cuda.synchronize(dev)
+        e2e16_s = time.perf_counter() - t0
+        e2e16_value = sharding.aggregate_rate(B * T_e * args.e2e_steps, world, sharding.max_over_ranks(e2e16_s, dev, dist))
+        sl = slice(0, None, 4801)
+        d16 = (yh16[:, :, sl].double() - yh[:, :, sl].double())
+        e2e16_esr = float((d16 ** 2).sum() / ((yh[:, :, sl].double() ** 2).sum() + 1e-12))
+        del xh, yh, xh16, yh16
 
         # ---- the same workload in the strict (fp32-grade) tensor-core mode, every rank its own shard ------------
         strict = strict_leg(model, x, args, dev, barrier, sharding, dist, world, lib)
@@ -359,7 +374,11 @@ def main():
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": B * T_e * 4,
                 "d2h_bytes_per_step": B * T_e * 4, "samples_per_stream": T_e, "finite": e2e_ok,
                 "api": "RNN.predict_host -> ntm_gru_predict_host (pinned host buffers)",
-                "rank0_numa_node": numa_node},
+                "rank0_numa_node": numa_node,
+                "f16_transport": {"value": e2e16_value, "unit": "samples/s", "h2d_bytes_per_step": B * T_e * 2,
+                                  "d2h_bytes_per_step": B * T_e * 2, "esr_vs_f32_transport_rank0": e2e16_esr,
+                                  "api": "RNN.predict_host(float16 host tensor) -> ntm_gru_predict_host_f16 (opt-in: binary16 "
+                                         "samples over the host link, same fp32-state kernels)"}},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {

@@ -153,6 +153,16 @@ int ntm_esr_sums(const float* out, int64_t ldo, const float* target, int64_t ldt
 int ntm_gru_predict_host(void* handle, int mode, const float* x_host, float* y_host, float* h_host,
                          int64_t B, int64_t T, int skip, int64_t chunk_T);
 
+/*
+ * The same with a 16-BIT HOST TRANSPORT (opt-in; no counterpart in the reference, whose audio is float32 end to end):
+ * x_host_f16 / y_host_f16 hold IEEE binary16 samples (B x T contiguous), cross the host link as such -- half the bytes per
+ * sample, which is what bounds the end-to-end rate once several GPUs share one host -- and are widened
+ * / narrowed on the device around the same fp32 kernels.  State in / out stays float32.  Cost in accuracy: the quantisation
+ * of the input and of the output to 11 significant bits (ESR ~1e-7 against the float32 transport, tests/test_host_f16_gpu.py).
+ */
+int ntm_gru_predict_host_f16(void* handle, int mode, const void* x_host_f16, void* y_host_f16, float* h_host,
+                             int64_t B, int64_t T, int skip, int64_t chunk_T);
+
 /* DiffDelRNN.predict (code/model.py:618-653) from HOST buffers; hist_host: B x D in-out. */
 int ntm_diffdel_predict_host(void* handle, int mode, const float* x_host, const float* d_host,
                              float* y_host, float* pre_d_host, float* h_host, float* hist_host,

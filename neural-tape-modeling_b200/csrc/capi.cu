@@ -159,12 +159,16 @@ int pipe_init(Handle* hd, size_t floats)
 }
 
 // Shared body of the two *_host entry points (d_host == nullptr: plain GRU).
+// half_io (plain GRU only): x_host / y_host hold IEEE binary16 samples; they cross the host link as such and are widened /
+// narrowed on the device (csrc/convert.cu) around the same fp32 kernels.
 int predict_host(Handle* hd, int mode, const float* x_host, const float* d_host, float* y_host, float* pre_host,
-                 float* h_host, float* hist_host, int64_t B, int64_t T, int64_t D, int skip, int64_t chunk_T)
+                 float* h_host, float* hist_host, int64_t B, int64_t T, int64_t D, int skip, int64_t chunk_T,
+                 bool half_io = false)
 {
     if (!x_host || !y_host || !h_host || B < 0 || T < 0) return NTM_EINVAL;
     const bool delay = d_host != nullptr;
     if (delay && (!pre_host || !hist_host || D < 0)) return NTM_EINVAL;
+    if (delay && half_io) return NTM_EUNSUPPORTED;
     if (!mode_supported(mode)) return NTM_EUNSUPPORTED;
     if (B == 0) return NTM_OK;
     DeviceGuard g(hd->device);
@@ -176,7 +180,7 @@ int predict_host(Handle* hd, int mode, const float* x_host, const float* d_host,
     if (C > T) C = (T + 63) & ~63ll;
     if (C == 0) C = 64;
     const size_t slab = (size_t)B * (size_t)C;
-    const size_t narr = delay ? 8 : 4;
+    const size_t narr = delay ? 8 : half_io ? 6 : 4;      // half_io: two more slabs hold the four binary16 staging arrays
     const size_t hfl = (size_t)B * 64, histfl = delay ? (size_t)B * (size_t)D : 0;
     int rc = pipe_init(hd, narr * slab + hfl + 2 * histfl + 64);
     if (rc != NTM_OK) return rc;
@@ -189,6 +193,15 @@ int predict_host(Handle* hd, int mode, const float* x_host, const float* d_host,
         dd[0] = p.buf + 4 * slab; dd[1] = p.buf + 5 * slab;
         dp[0] = p.buf + 6 * slab; dp[1] = p.buf + 7 * slab;
     }
+    // binary16 staging (slab elements = half a float slab each): in[2], out[2]
+    uint16_t* hx[2] = {nullptr, nullptr};
+    uint16_t* hy[2] = {nullptr, nullptr};
+    if (half_io) {
+        uint16_t* hb = reinterpret_cast<uint16_t*>(p.buf + 4 * slab);
+        hx[0] = hb; hx[1] = hb + slab; hy[0] = hb + 2 * slab; hy[1] = hb + 3 * slab;
+    }
+    const uint16_t* x16 = reinterpret_cast<const uint16_t*>(x_host);
+    uint16_t* y16 = reinterpret_cast<uint16_t*>(y_host);
     float* dh = p.buf + narr * slab;
     float* dhist[2] = {dh + hfl, dh + hfl + histfl};
 
@@ -203,8 +216,11 @@ int predict_host(Handle* hd, int mode, const float* x_host, const float* d_host,
         const int k = (int)(c & 1);
         // host -> device (stream s_in); the staging slot is free once the kernel of chunk c-2 finished
         if (c >= 2) CU(cudaStreamWaitEvent(p.s_in, p.ev_run[k], 0));
-        CU(cudaMemcpy2DAsync(dx[k], C * sizeof(float), x_host + t0, T * sizeof(float), n * sizeof(float), B,
-                             cudaMemcpyHostToDevice, p.s_in));
+        if (half_io)
+            CU(cudaMemcpy2DAsync(hx[k], C * 2, x16 + t0, T * 2, n * 2, B, cudaMemcpyHostToDevice, p.s_in));
+        else
+            CU(cudaMemcpy2DAsync(dx[k], C * sizeof(float), x_host + t0, T * sizeof(float), n * sizeof(float), B,
+                                 cudaMemcpyHostToDevice, p.s_in));
         if (delay)
             CU(cudaMemcpy2DAsync(dd[k], C * sizeof(float), d_host + t0, T * sizeof(float), n * sizeof(float), B,
                                  cudaMemcpyHostToDevice, p.s_in));
@@ -220,13 +236,18 @@ int predict_host(Handle* hd, int mode, const float* x_host, const float* d_host,
             a.hist_in = dhist[hcur]; a.hist_out = dhist[hcur ^ 1];
             hcur ^= 1;
         }
+        if (half_io) CU(ntm::launch_half_to_float(hx[k], dx[k], (long long)slab, hd->sm_count, p.s_run));
         rc = run_gru(hd, mode, a, p.s_run);
         if (rc != NTM_OK) return rc;
+        if (half_io) CU(ntm::launch_float_to_half(dy[k], hy[k], (long long)slab, hd->sm_count, p.s_run));
         CU(cudaEventRecord(p.ev_run[k], p.s_run));
         // device -> host (stream s_out)
         CU(cudaStreamWaitEvent(p.s_out, p.ev_run[k], 0));
-        CU(cudaMemcpy2DAsync(y_host + t0, T * sizeof(float), dy[k], C * sizeof(float), n * sizeof(float), B,
-                             cudaMemcpyDeviceToHost, p.s_out));
+        if (half_io)
+            CU(cudaMemcpy2DAsync(y16 + t0, T * 2, hy[k], C * 2, n * 2, B, cudaMemcpyDeviceToHost, p.s_out));
+        else
+            CU(cudaMemcpy2DAsync(y_host + t0, T * sizeof(float), dy[k], C * sizeof(float), n * sizeof(float), B,
+                                 cudaMemcpyDeviceToHost, p.s_out));
         if (delay)
             CU(cudaMemcpy2DAsync(pre_host + t0, T * sizeof(float), dp[k], C * sizeof(float), n * sizeof(float), B,
                                  cudaMemcpyDeviceToHost, p.s_out));
@@ -632,6 +653,15 @@ int ntm_gru_predict_host(void* handle, int mode, const float* x_host, float* y_h
     Handle* hd = as_handle(handle);
     if (!hd) return NTM_EINVAL;
     return predict_host(hd, mode, x_host, nullptr, y_host, nullptr, h_host, nullptr, B, T, 0, skip, chunk_T);
+}
+
+int ntm_gru_predict_host_f16(void* handle, int mode, const void* x_host_f16, void* y_host_f16, float* h_host, int64_t B,
+                             int64_t T, int skip, int64_t chunk_T)
+{
+    Handle* hd = as_handle(handle);
+    if (!hd) return NTM_EINVAL;
+    return predict_host(hd, mode, static_cast<const float*>(x_host_f16), nullptr, static_cast<float*>(y_host_f16), nullptr,
+                        h_host, nullptr, B, T, 0, skip, chunk_T, true);
 }
 
 int ntm_diffdel_predict_host(void* handle, int mode, const float* x_host, const float* d_host, float* y_host,

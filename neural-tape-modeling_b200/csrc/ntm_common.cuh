@@ -100,6 +100,10 @@ cudaError_t launch_delay(const float* x, long long ldx, const float* d, long lon
 cudaError_t launch_delay_check(const float* d, long long ldd, long long B, long long T, long long D, int* flag_dev,
                                cudaStream_t st);
 
+// 16-bit host transport: n elements (a multiple of 8), 16-byte aligned buffers
+cudaError_t launch_half_to_float(const void* src, float* dst, long long n, int sm_count, cudaStream_t st);
+cudaError_t launch_float_to_half(const float* src, void* dst, long long n, int sm_count, cudaStream_t st);
+
 // per_row == 0: sums[2] over all B x T samples; per_row != 0: sums[B][2], row b over samples [first[b], first[b] + count[b])
 // (first / count: device arrays or nullptr = 0 / T)
 cudaError_t launch_esr(const float* out, long long ldo, const float* tgt, long long ldt, long long B, long long T,

@@ -42,6 +42,7 @@ SIGNATURES = {
     "ntm_delay_forward": (_int, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _int, _int, _vp]),
     "ntm_delay_check": (_int, [_vp, _i64, _i64, _i64, _i64, _int, _vp]),
     "ntm_gru_predict_host": (_int, [_vp, _int, _vp, _vp, _vp, _i64, _i64, _int, _i64]),
+    "ntm_gru_predict_host_f16": (_int, [_vp, _int, _vp, _vp, _vp, _i64, _i64, _int, _i64]),
     "ntm_diffdel_predict_host": (_int, [_vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _i64]),
     "ntm_set_tuning": (_int, [_int, _int]),
     "ntm_rt_open": (_int, [_vp, _int, _vp, _i64, _i64, _int, _int, ctypes.POINTER(_vp)]),

@@ -38,12 +38,12 @@ def _stream(device):
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
-def _host_out(out, shape, name):
-    """Result buffer of a *_host call: a fresh pinned tensor, or the caller's contiguous float32 host tensor."""
+def _host_out(out, shape, name, dtype=torch.float32):
+    """Result buffer of a *_host call: a fresh pinned tensor, or the caller's contiguous host tensor of that dtype."""
     if out is None:
-        return torch.empty(shape, dtype=torch.float32, pin_memory=True)
-    if out.is_cuda or out.dtype != torch.float32 or tuple(out.shape) != tuple(shape) or not out.is_contiguous():
-        raise RuntimeError(f"{name}: expected a contiguous float32 host tensor of shape {tuple(shape)}")
+        return torch.empty(shape, dtype=dtype, pin_memory=True)
+    if out.is_cuda or out.dtype != dtype or tuple(out.shape) != tuple(shape) or not out.is_contiguous():
+        raise RuntimeError(f"{name}: expected a contiguous {dtype} host tensor of shape {tuple(shape)}")
     return out
 
 
@@ -242,19 +242,24 @@ class RNN(torch.nn.Module):
         """predict() for a HOST tensor (pinned for full speed): chunked H2D / kernel / D2H pipeline inside the
         engine (ntm_gru_predict_host).  Returns a pinned host tensor (`out` if given: page-locking a fresh
         multi-GB result buffer costs seconds, so repeated callers pass their own).  This is the end-to-end call the
-        bench times (host->device at code/test-model.py:427-433, device->host at :525)."""
+        bench times (host->device at code/test-model.py:427-433, device->host at :525).
+
+        A float16 `input` selects the opt-in 16-bit host transport (ntm_gru_predict_host_f16): the samples cross the
+        host link as binary16 -- half the bytes -- and the result comes back as float16; arithmetic and state stay as
+        `mode` says."""
         if input.is_cuda or input.dim() != 3 or input.shape[1] != 1:
             raise RuntimeError("predict_host expects a host tensor of shape (N_BATCHES, 1, N_SAMPLES)")
         dev = self._device()
         handle = self._handle(dev)
-        x = input.float().contiguous()
+        half = input.dtype == torch.float16
+        x = input.contiguous() if half else input.float().contiguous()
         B, T = x.shape[0], x.shape[2]
         self.initialize_hidden()
         self.warm_start()
         h = self.hidden.reshape(1, self.hidden_size).expand(B, self.hidden_size).contiguous().cpu()
-        y = _host_out(out, (B, 1, T), "out")
-        rc = _lib.load().ntm_gru_predict_host(handle, _lib.MODES[self.mode], _ptr(x), _ptr(y), _ptr(h), B, T,
-                                              int(bool(self.skip)), int(chunk))
+        y = _host_out(out, (B, 1, T), "out", torch.float16 if half else torch.float32)
+        fn = _lib.load().ntm_gru_predict_host_f16 if half else _lib.load().ntm_gru_predict_host
+        rc = fn(handle, _lib.MODES[self.mode], _ptr(x), _ptr(y), _ptr(h), B, T, int(bool(self.skip)), int(chunk))
         _lib.check(rc)
         self.hidden = h.reshape(1, B, self.hidden_size).to(dev)
         return y
