@@ -13,6 +13,9 @@ import os
 import sys
 import time
 
+import ctypes
+import glob
+
 import torch
 import torch.distributed as dist
 
@@ -33,21 +36,58 @@ s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
 nbytes = B * T * 4
 
 
+# cudaMemcpy2DAsync straight from the CUDA runtime torch already loaded (torch's own copy_ of a strided host view goes through a
+# CPU-side repack, which is not what the engine's pipeline does: csrc/capi.cu predict_host)
+_cands = glob.glob(os.path.join(os.path.dirname(torch.__file__), "..", "nvidia", "cuda_runtime", "lib", "libcudart.so*")) + ["libcudart.so.12", "libcudart.so"]
+for _c in _cands:
+    try:
+        cudart = ctypes.CDLL(_c)
+        break
+    except OSError:
+        cudart = None
+assert cudart is not None, "libcudart not found"
+cudart.cudaMemcpy2DAsync.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t,
+                                     ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]
+cudart.cudaMemcpy2DAsync.restype = ctypes.c_int
+
+
+def copy2d(dst, dpitch, src, spitch, width, height, kind, stream):
+    rc = cudart.cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, kind, stream.cuda_stream)
+    assert rc == 0, f"cudaMemcpy2DAsync -> {rc}"
+
+
 def h2d():
-    with torch.cuda.stream(s_in):
-        for c in range(T // C):
-            stage_in[c & 1].copy_(xh[:, c * C:(c + 1) * C], non_blocking=True)
+    for c in range(T // C):
+        copy2d(stage_in[c & 1].data_ptr(), C * 4, xh.data_ptr() + c * C * 4, T * 4, C * 4, B, 1, s_in)
 
 
 def d2h():
-    with torch.cuda.stream(s_out):
-        for c in range(T // C):
-            yh[:, c * C:(c + 1) * C].copy_(stage_out[c & 1], non_blocking=True)
+    for c in range(T // C):
+        copy2d(yh.data_ptr() + c * C * 4, T * 4, stage_out[c & 1].data_ptr(), C * 4, C * 4, B, 2, s_out)
 
 
 def both():
     h2d()
     d2h()
+
+
+big_in = torch.empty((B, T), dtype=torch.float32, device=dev)
+big_out = torch.zeros((B, T), dtype=torch.float32, device=dev)
+
+
+def h2d_1d():                               # one contiguous cudaMemcpyAsync of the whole buffer
+    with torch.cuda.stream(s_in):
+        big_in.copy_(xh, non_blocking=True)
+
+
+def d2h_1d():
+    with torch.cuda.stream(s_out):
+        yh.copy_(big_out, non_blocking=True)
+
+
+def both_1d():
+    h2d_1d()
+    d2h_1d()
 
 
 def timed(fn, active):
@@ -65,12 +105,15 @@ def timed(fn, active):
 
 
 if rank == 0:
-    print(f"# {world} ranks available, {nbytes/1e9:.2f} GB per direction and rank, 2-D chunks of {C} samples x {B} rows, host cpus {os.cpu_count()}")
+    print(f"# {world} ranks available, {nbytes/1e9:.2f} GB per direction and rank, host cpus {os.cpu_count()}; GB/s per active rank (min, mean) and "
+          f"summed over the active ranks; H2D / D2H: cudaMemcpy2DAsync in chunks of {C} samples x {B} rows (the engine's pipeline), 1-D: one "
+          f"contiguous cudaMemcpyAsync; H2D+D2H: both directions at once, bytes of both counted")
 k = 1
 while k <= world:
     active = rank < k
     row = []
-    for name, fn, mult in (("H2D", h2d, 1), ("D2H", d2h, 1), ("H2D+D2H", both, 2)):
+    for name, fn, mult in (("H2D", h2d, 1), ("D2H", d2h, 1), ("H2D+D2H", both, 2), ("1-D H2D", h2d_1d, 1), ("1-D D2H", d2h_1d, 1),
+                           ("1-D H2D+D2H", both_1d, 2)):
         dist.barrier()
         # warm-up pass and the timed pass are both inside timed(); the two barriers keep idle ranks in step
         dt = timed(fn, active)
@@ -78,7 +121,7 @@ while k <= world:
         rates = [torch.zeros(1, dtype=torch.float64) for _ in range(world)]
         dist.all_gather(rates, rate)
         r = [float(v) for v in rates[:k]]
-        row.append(f"{name}: per rank min {min(r):5.1f} mean {sum(r)/k:5.1f} GB/s, aggregate {sum(r):6.1f}")
+        row.append(f"{name}: min {min(r):5.1f} mean {sum(r)/k:5.1f} sum {sum(r):6.1f}")
     if rank == 0:
         print(f"{k} active rank(s) | " + " | ".join(row), flush=True)
     k *= 2
