@@ -72,7 +72,11 @@ def test_tc_predict_esr_vs_golden(tag, mode, kernel):
                 assert c_oracle.esr(y, ref) <= ESR_TOL, (tag, mode, sig, c_oracle.esr(y, ref))
                 assert np.max(np.abs(y - ref)) <= 5e-3, (tag, mode, sig)
             else:
-                assert np.all(np.isfinite(y)) and np.max(np.abs(y - ref)) <= 5e-2, (tag, mode, sig)
+                # the checkpoint amplifies round-off on this signal: the reference's own fp32-vs-fp64 distance (`floor`) is what
+                # an operand unit round-off of 2^-24 grows to, so 11-bit operands (2^-11: 2^13 times coarser) may grow to
+                # half of 2^13 floors (achieved: <= 1560 floors, profiles/r02_parity.json)
+                bound = min(5e-2, 4096.0 * float(g[f"floor_{sig}"]))
+                assert np.all(np.isfinite(y)) and np.max(np.abs(y - ref)) <= bound, (tag, mode, sig, np.max(np.abs(y - ref)), bound)
 
 
 def test_bf16_is_finite_and_close():
@@ -80,7 +84,7 @@ def test_bf16_is_finite_and_close():
     g = load_golden("golden_cfg2")
     with torch.inference_mode():
         y = m.predict(dev(g["x_sweepnoise_lo"]).reshape(1, 1, -1)).cpu().numpy().reshape(-1)
-    assert np.all(np.isfinite(y)) and c_oracle.esr(y, g["y_sweepnoise_lo"]) <= 5e-2
+    assert np.all(np.isfinite(y)) and c_oracle.esr(y, g["y_sweepnoise_lo"]) <= 1e-2     # (achieved 4e-3: 8-bit significand)
 
 
 @pytest.mark.parametrize("mode", TC_MODES)
