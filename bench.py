@@ -645,14 +645,18 @@ def aux_measurements(ntm_b200, signals, dev, mode):
         big[str(Bb)]["fp32_cuda_core"] = timed(xb, mb)
         del xb
     # roofline of the throughput regime at the balanced width: tensor FLOP/s against the measured dense peak, and the
-    # MUFU bound of the stream-major kernel (4 MUFU per unit-step: 3 ex2 + 2 shared reciprocals / 2)
+    # MUFU bound of the stream-major kernel
     bal = big[str(sms * 256)]["auto"]
     tensor_peak = measured_peaks()[0]
     out["large_batch_roofline"] = {
         "streams": sms * 256, "samples_per_s": bal, "kernel": big[str(sms * 256)]["auto_kernel"],
         "tensor_tflops": bal * FLOP_PER_SAMPLE / 1e12, "frac_of_measured_bf16_peak": bal * FLOP_PER_SAMPLE / 1e12 / tensor_peak,
-        "mufu_bound_samples_per_s_at_max_clock": sms * 16 * 1.965e9 / (64 * 4.0),
-        "frac_of_mufu_bound": bal / (sms * 16 * 1.965e9 / (64 * 4.0))}
+        # MUFU work of the stream-major kernel: 3 ex2 per unit-step + the r/z reciprocal shared by two units + the n reciprocal
+        # shared by four = 3.75 MUFU per unit-step (f16 / bf16 operands) at 16 lanes per clock and SM
+        "mufu_per_unit_step": 3.75,
+        "mufu_bound_samples_per_s_at_max_clock": sms * 16 * 1.965e9 / (64 * 3.75),
+        "frac_of_mufu_bound": bal / (sms * 16 * 1.965e9 / (64 * 3.75)),
+        "frac_of_round1_mufu_bound_4_per_unit": bal / (sms * 16 * 1.965e9 / (64 * 4.0))}
     out["large_batch_samples_per_s"] = big
     # cfg 3: DiffDelGRU (GRU + fused fractional-delay read), 256 streams x 30 s, predict() semantics
     Bd, Td = 256, 30 * FS

@@ -17,8 +17,8 @@
 //   epilogue   accumulator lane = stream, column = gate row: TWO THREADS OWN ONE STREAM (32 hidden units each) -- their
 //              fp32 states live in registers for the whole launch, r/z/n of every unit arrive by tcgen05.ld, per-unit
 //              constants are warp-uniform (kernel-parameter constant bank), the output head is an in-thread fp32 dot
-//              product, reciprocals are shared between the r and z gates of two units and the n gates of two units
-//              (4.0 MUFU per unit-step, gates.cuh).
+//              product, reciprocals are shared between the r and z gates of two units and the n gates of four units
+//              (3.75 MUFU per unit-step; 4.0 in the formats without the K augmentation, gates.cuh).
 // Operand formats (template FMT):
 //   f16 / bf16   K = 80: [H | x_hi x_lo x_hi 1 1 0..]: the K augmentation carries W_i x + b (r, z) and b_hn (n) through the MMA
 //   f16x3        STRICT, fp32-grade: K = 192 = [h_hi | h_lo' | h_hi] . [G W_hi | G W_hi / 2^8 | (G W)_lo]^T with
@@ -57,7 +57,8 @@ constexpr float TS_LO_SCALE = 256.0f;      // strict form: h_lo' = (h - h_hi) * 
 // golden signal: 3.3e-5 either way) and cost 16 % (9.18 vs 10.96 Gsamples/s at 37 888 streams) -- sharing stays.
 #define NTM_TCS_STRICT_OWN_RCP 0
 #endif
-constexpr int TCS_DEFAULT_VAR = 7;         // staggered tiles + reciprocal shared by two units + packed fp32 arithmetic
+constexpr int TCS_DEFAULT_VAR = 15;        // staggered tiles + r/z reciprocal shared by two units + packed fp32 arithmetic + n reciprocal
+                                           // shared by four units (the last only where the K augmentation exists: f16, bf16)
 
 template <int FMT>
 struct TsFmt {
@@ -248,6 +249,53 @@ __device__ __forceinline__ void tcs_gate_pair(const TcsConsts& kc, int j, float 
     }
 }
 
+// FOUR hidden units (j .. j+3) of one stream, AUG formats, packed arithmetic: r and z of each pair share a reciprocal (as in
+// tcs_gate_pair, SHARE4), and the n gates of all four units share ONE (3.75 MUFU per unit-step instead of 4.0; ex2 arguments of n
+// clamped to 30 so that the product of four denominators stays below 2^121: tanh saturates at 1 - 2^-29).  Measured at 37 888
+// streams (profiles/r02_tcs_quad.txt): 19.44 vs 20.08 clk per stream-step per SM; taking the second pair's z-gate 2^x from the FMA
+// pipe on top (3.25 MUFU per unit-step, 12 more instructions per quad) gave 19.32 -- the MUFU pipe is no longer the bound, not kept.
+__device__ __forceinline__ void tcs_gate_quad(const TcsConsts& kc, int j, float x, const float (&ar)[4], const float (&az)[4],
+                                              const float (&an)[4], float* h, float& ys0, float& ys1)
+{
+    constexpr float C = 30.0f;
+    const f32x2 one = pk(1.0f, 1.0f), x2 = pk(x, x);
+    f32x2 z[2], dn[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int jj = j + 2 * q;
+        const f32x2 dr = add2(pk(ex2_approx(fminf(ar[2 * q], C)), ex2_approx(fminf(ar[2 * q + 1], C))), one);
+        const f32x2 dz = add2(pk(ex2_approx(fminf(az[2 * q], C)), ex2_approx(fminf(az[2 * q + 1], C))), one);
+        const f32x2 p = mul2(dr, dz);
+        float p0, p1;
+        upk(p, p0, p1);
+        const float qi = rcp_approx(p0 * p1);
+        const f32x2 inv = mul2(pk(p1, p0), pk(qi, qi));
+        const f32x2 r = mul2(dz, inv);
+        z[q] = mul2(dr, inv);
+        const f32x2 gin = fma2(pk(kc.cn_w[jj], kc.cn_w[jj + 1]), x2, pk(kc.cn_b[jj], kc.cn_b[jj + 1]));
+        float a0, a1;
+        upk(fma2(r, pk(an[2 * q], an[2 * q + 1]), gin), a0, a1);
+        dn[q] = add2(pk(ex2_approx(fminf(a0, C)), ex2_approx(fminf(a1, C))), one);
+    }
+    float d0, d1, d2, d3;
+    upk(dn[0], d0, d1);
+    upk(dn[1], d2, d3);
+    const float pa = d0 * d1, pb = d2 * d3;
+    const float qn = rcp_approx(pa * pb);
+    const float ia = pb * qn, ib = pa * qn;                      // 1 / (d0 d1), 1 / (d2 d3)
+    const f32x2 m2 = pk(-2.0f, -2.0f), m1 = pk(-1.0f, -1.0f);
+    const f32x2 n0 = fma2(mul2(pk(d1, d0), pk(ia, ia)), m2, one);          // 1 - 2 / dn
+    const f32x2 n1 = fma2(mul2(pk(d3, d2), pk(ib, ib)), m2, one);
+    const f32x2 h0 = fma2(z[0], fma2(n0, m1, pk(h[0], h[1])), n0);         // n + z (h - n)
+    const f32x2 h1 = fma2(z[1], fma2(n1, m1, pk(h[2], h[3])), n1);
+    upk(h0, h[0], h[1]);
+    upk(h1, h[2], h[3]);
+    ys0 = fmaf(kc.wo[j], h[0], ys0);
+    ys0 = fmaf(kc.wo[j + 1], h[1], ys0);
+    ys1 = fmaf(kc.wo[j + 2], h[2], ys1);
+    ys1 = fmaf(kc.wo[j + 3], h[3], ys1);
+}
+
 // Publish the (rounded) states of TS_UG consecutive units, first unit `jl` of this thread's slice, into the tile's A operand.
 template <int FMT>
 __device__ __forceinline__ void tcs_store_state(uint32_t t_op, int u0, int jl, const float* h)
@@ -287,6 +335,8 @@ __device__ __forceinline__ void tcs_epilogue(const GruArgs& a, const TcsConsts& 
     // (the strict form shares a reciprocal only between the r and z gate of ONE unit: a product of four denominators
     // carries three more roundings into every gate value)
     constexpr bool STAGGER = (VAR & 1) != 0 && TILES == 2, SHARE4 = (VAR & 2) != 0 && !F::STRICT, PACK2 = (VAR & 4) != 0;
+    // bit 3: the n gates of four units share one reciprocal (3.75 MUFU per unit-step; formats with the K augmentation only)
+    constexpr bool QUAD = (VAR & 8) != 0 && F::AUG && SHARE4 && PACK2;
     constexpr int NU = 64 / TS_UW;               // hidden units per thread
     constexpr int NG = NU / TS_UG;               // TMEM load groups per thread and step
     constexpr int u0 = UH * NU;
@@ -366,11 +416,22 @@ __device__ __forceinline__ void tcs_epilogue(const GruArgs& a, const TcsConsts& 
                 tmem_ld8(t_acc + 64 + u0 + (g + 1) * TS_UG, acc[1]);
                 tmem_ld8(t_acc + 128 + u0 + (g + 1) * TS_UG, acc[2]);
             }
+            if (QUAD) {
+#pragma unroll
+                for (int q = 0; q < TS_UG / 4; ++q) {
+                    const int jl = g * TS_UG + 4 * q;
+                    const float qr[4] = {pre[0][4 * q], pre[0][4 * q + 1], pre[0][4 * q + 2], pre[0][4 * q + 3]};
+                    const float qz[4] = {pre[1][4 * q], pre[1][4 * q + 1], pre[1][4 * q + 2], pre[1][4 * q + 3]};
+                    const float qn[4] = {pre[2][4 * q], pre[2][4 * q + 1], pre[2][4 * q + 2], pre[2][4 * q + 3]};
+                    tcs_gate_quad(kc, u0 + jl, x0, qr, qz, qn, &h[jl], ys[0], ys[1]);
+                }
+            } else {
 #pragma unroll
             for (int p = 0; p < TS_UG / 2; ++p) {
                 const int jl = g * TS_UG + 2 * p;                      // local unit index; global = u0 + jl (static per UH)
                 tcs_gate_pair<FMT, SHARE4, PACK2>(kc, u0 + jl, x0, pre[0][2 * p], pre[0][2 * p + 1], pre[1][2 * p],
                                                   pre[1][2 * p + 1], pre[2][2 * p], pre[2][2 * p + 1], h[jl], h[jl + 1], ys[p & 1]);
+            }
             }
             tcs_store_state<FMT>(t_op, u0, g * TS_UG, h);
             if (g == NG / 2 - 1) TCS_STAMP(1);
@@ -694,8 +755,9 @@ cudaError_t launch_tcs_var(const GruArgs& a, const TcsConsts& kc, int var, int s
 {
     const bool dynamic = var < 0 || (var & 32) == 0;
     if (var >= 0) var &= 31;
-    switch (var) {      // experiments: (var & 7) = VAR bits, (var & 32) = static schedule
+    switch (var) {      // experiments: (var & 15) = VAR bits, (var & 32) = static schedule
         case 3: return launch_tcs_one<FMT, TILES, 3>(a, kc, sm_count, dynamic, st);
+        case 7: if (FMT < 2) return launch_tcs_one<FMT < 2 ? FMT : 0, TILES, 7>(a, kc, sm_count, dynamic, st);      // (elsewhere 7 == 15)
         default: return launch_tcs_one<FMT, TILES, TCS_DEFAULT_VAR>(a, kc, sm_count, dynamic, st);
     }
 }

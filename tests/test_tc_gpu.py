@@ -249,7 +249,7 @@ def test_stream_major_dynamic_schedule_is_exact():
         for tiles, B, T in ((2, sms * 256 + 300, 700), (1, sms * 128 + 1000, 900)):
             x = signals.stream_batch_device(B, T, DEV, dur=10.0).reshape(B, 1, T)
             outs = []
-            for var in (7, 39):                                   # default variant: dynamic, static (bit 32)
+            for var in (15, 47):                                  # default variant: dynamic, static (bit 32)
                 lib.load().ntm_set_tuning(tiles + 4 * (var + 1), 4)
                 m.hidden = hw.expand(1, B, 64).contiguous()
                 outs.append((m(x), m.hidden.clone()))
