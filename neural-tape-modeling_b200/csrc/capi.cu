@@ -116,12 +116,12 @@ int run_gru(Handle* hd, int mode, const ntm::GruArgs& a, cudaStream_t st)
             CU(ntm::launch_gru_tcs(a, hd->tcs, fmt, hd->sm_count, tg == 4 ? (tune.s & 3) : 0, tg == 4 ? (tune.s >> 2) - 1 : -1, st));
             kernel = 3;
         } else {
-            // automatic: 4 streams per CTA (shorter dependent step) up to two such CTAs per SM -- measured 221 vs 243
-            // ns/step at 1024 streams, 177 vs 238 at <= 592 (profiles/r02_g2_check.txt); the strict form is tensor-pipe
-            // bound and wastes nothing on dead columns beyond one CTA per SM
+            // automatic: 4 streams per CTA (shorter dependent step) up to two such CTAs per SM -- measured 216 vs 243
+            // ns/step at 1024 streams, 172 vs 238 at <= 592 (profiles/r02_mma_variants.txt); the strict form too since its
+            // 4-stream layout carries the state residual in the otherwise dead columns (two MMAs per product instead of
+            // three): 363 vs 394 ns/step at 1024 streams, 264 vs 388 at batch 1 (profiles/r02_strict_paircol.txt)
             int nt;
             if (tune.s > 0 && tg == 3) nt = tune.s / 8;
-            else if (fmt == 3) nt = a.B <= 4ll * hd->sm_count ? 0 : 1;
             else nt = a.B <= 8ll * hd->sm_count ? 0 : 1;
             CU(ntm::launch_gru_mma(a, fmt, nt, st));
             kernel = 1;

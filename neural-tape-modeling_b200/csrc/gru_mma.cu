@@ -64,6 +64,12 @@ __global__ void __launch_bounds__(128, (FMT == FMT_TF32 || HALF || SPLIT) ? 2 : 
     static_assert(!SPLIT || (FMT == FMT_F16 && NT == 1 && !DEFER), "the strict form: f16 pairs, one n8 tile, immediate head");
     constexpr int NP = SPLIT ? 2 : 1;                // operand parts (hi, lo')
     constexpr int SL = SPLIT ? 1 : 0;                // accumulators per tile: W_hi h_hi | (strict) W_hi h_lo' , W_lo' h_hi
+    // PAIRCOL: strict form with four streams per CTA.  The odd column next to a stream's even column, dead in the rounded
+    // modes, carries the stream's scaled residual h_lo': ONE MMA with W_hi then yields W_hi h_hi (even column) and W_hi h_lo'
+    // (odd column) and a second one with W_lo' yields W_lo' h_hi -- two MMAs per product instead of three, one set of B
+    // fragments, one head MMA (row 0 = w_hi, row 8 = w_lo': c0 + 2^-11 (c1 + c2)).  25 HMMAs per warp and step instead of 38.
+    constexpr bool PAIRCOL = SPLIT && HALF;
+    constexpr int NPB = PAIRCOL ? 1 : NP;            // parts of the state tile a thread loads B fragments from
     constexpr int SC = HALF ? 4 : 8 * NT;            // streams per CTA
     constexpr int CS = HALF ? 2 : 1;                 // column stride of a stream
     constexpr int NE = HALF ? 1 : 2;                 // live columns per thread and n8 tile
@@ -164,12 +170,12 @@ __global__ void __launch_bounds__(128, (FMT == FMT_TF32 || HALF || SPLIT) ? 2 : 
         }
     }
     // this warp's k-steps of the B fragments (warp-uniform selects; a dynamic index would spill the array)
-    auto head_mma = [&](const uint32_t (&bp)[NP][BW], float (&c)[4]) {
+    auto head_mma = [&](const uint32_t (&bp)[NPB][BW], float (&c)[4]) {
         c[0] = c[1] = c[2] = c[3] = 0.0f;
 #pragma unroll
         for (int q = 0; q < HK; ++q) {
 #pragma unroll
-            for (int part = 0; part < NP; ++part) {
+            for (int part = 0; part < NPB; ++part) {
                 const uint32_t (&b)[BW] = bp[part];
                 uint32_t b0, b1;
                 if (HK == 1) {
@@ -190,20 +196,34 @@ __global__ void __launch_bounds__(128, (FMT == FMT_TF32 || HALF || SPLIT) ? 2 : 
     };
     // the two columns of a head tile -> the samples of streams 2tig, 2tig + 1
     auto head_value = [&](const float (&c)[4]) {
+        if (PAIRCOL) return make_float2(fmaf(SPLIT_INV, c[1] + c[2], c[0]), 0.0f);
         return SPLIT ? make_float2(fmaf(SPLIT_INV, c[2], c[0]), fmaf(SPLIT_INV, c[3], c[1])) : make_float2(c[0] + c[2], c[1] + c[3]);
     };
-    auto load_bfrag = [&](const uint8_t* tile, int nt, uint32_t (&bp)[NP][BW]) {
+    auto load_bfrag = [&](const uint8_t* tile, int nt, uint32_t (&bp)[NPB][BW]) {
         // f16/bf16: the thread's 16 elements are contiguous (2 vectors); tf32: vector q holds elements
         // q*16 + tig*4 .. +3 (4 vectors, a quarter-warp reads 64 contiguous bytes); strict form: the lo' part of the row
         // follows the hi part
 #pragma unroll
-        for (int part = 0; part < NP; ++part) {
+        for (int part = 0; part < NPB; ++part) {
             const uint8_t* src = tile + (nt * 8 + gid) * F::ROW_BYTES + part * F::PART_BYTES + (FMT == FMT_TF32 ? tig * 16 : tig * 32);
 #pragma unroll
             for (int q = 0; q < BW / 4; ++q) {
                 const uint4 v = *reinterpret_cast<const uint4*>(src + q * (FMT == FMT_TF32 ? 64 : 16));
                 bp[part][4 * q] = v.x; bp[part][4 * q + 1] = v.y; bp[part][4 * q + 2] = v.z; bp[part][4 * q + 3] = v.w;
             }
+        }
+    };
+
+    // rounded state of units (u0, u0 + 1) of the stream in column `col` of a state tile
+    auto put_state = [&](uint8_t* tile, int col, float v0, float v1) {
+        if (PAIRCOL) {                                 // hi pair -> the stream's own column, scaled residual pair -> the next one
+            const __half2 hi = __floats2half2_rn(v0, v1);
+            const float2 hf = __half22float2(hi);
+            const __half2 lo = __floats2half2_rn((v0 - hf.x) * SPLIT_SCALE, (v1 - hf.y) * SPLIT_SCALE);
+            *reinterpret_cast<uint32_t*>(tile + col * F::ROW_BYTES + u0 * 2) = *reinterpret_cast<const uint32_t*>(&hi);
+            *reinterpret_cast<uint32_t*>(tile + (col + 1) * F::ROW_BYTES + u0 * 2) = *reinterpret_cast<const uint32_t*>(&lo);
+        } else {
+            store_state2<FMT, SPLIT>(tile + col * F::ROW_BYTES, u0, v0, v1);
         }
     };
 
@@ -258,8 +278,10 @@ __global__ void __launch_bounds__(128, (FMT == FMT_TF32 || HALF || SPLIT) ? 2 : 
             const bool live = col % CS == 0 && s < ns;
 #pragma unroll
             for (int u = 0; u < 2; ++u) hst[nt][u][e] = (live && a.h_in) ? a.h_in[(b0 + s) * 64 + u0 + u] : 0.0f;
-            store_state2<FMT, SPLIT>(hb + col * F::ROW_BYTES, u0, hst[nt][0][e], hst[nt][1][e]);
-            store_state2<FMT, SPLIT>(hb + C::HB_BYTES + col * F::ROW_BYTES, u0, 0.0f, 0.0f);     // dead columns stay finite
+            if (!PAIRCOL || e == 0) {
+                put_state(hb, col, hst[nt][0][e], hst[nt][1][e]);
+                put_state(hb + C::HB_BYTES, col, 0.0f, 0.0f);                                    // dead columns stay finite
+            }
         }
     const long long nchunks = (a.T + CH - 1) / CH;
     int cur = 0;
@@ -319,7 +341,7 @@ __global__ void __launch_bounds__(128, (FMT == FMT_TF32 || HALF || SPLIT) ? 2 : 
             uint8_t* hnext = hb + (cur ^ 1) * C::HB_BYTES;
             float acc[NT][3][4];
             float accs[SPLIT ? NT : 1][3][SPLIT ? 2 : 1][4];      // strict form: W_hi h_lo' and W_lo' h_hi (scaled by 2^11)
-            uint32_t breg[NT][NP][BW];
+            uint32_t breg[NT][NPB][BW];
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) {
                 load_bfrag(hcur, nt, breg[nt]);
@@ -355,7 +377,8 @@ __global__ void __launch_bounds__(128, (FMT == FMT_TF32 || HALF || SPLIT) ? 2 : 
                 for (int nt = 0; nt < NT; ++nt) {
                     mma_sync<FMT>(acc[nt][tile], areg[0][tile][ks], breg[nt][0][2 * ks], breg[nt][0][2 * ks + 1]);
                     if (SPLIT) {
-                        mma_sync<FMT>(accs[nt][tile][0], areg[0][tile][ks], breg[nt][NP - 1][2 * ks], breg[nt][NP - 1][2 * ks + 1]);
+                        if (!PAIRCOL)
+                            mma_sync<FMT>(accs[nt][tile][0], areg[0][tile][ks], breg[nt][NPB - 1][2 * ks], breg[nt][NPB - 1][2 * ks + 1]);
                         mma_sync<FMT>(accs[nt][tile][SL], areg[NP - 1][tile][ks], breg[nt][0][2 * ks], breg[nt][0][2 * ks + 1]);
                     }
                 }
@@ -399,8 +422,12 @@ __global__ void __launch_bounds__(128, (FMT == FMT_TF32 || HALF || SPLIT) ? 2 : 
                     for (int tile = 0; tile < 3; ++tile)
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
-                            if (!HALF || (i & 1) == 0)
+                            if (PAIRCOL) {             // W_hi h_lo' sits in the odd column of the main accumulator
+                                if ((i & 1) == 0)
+                                    acc[nt][tile][i] = fmaf(SPLIT_INV, acc[nt][tile][i + 1] + accs[nt][tile][SL][i], acc[nt][tile][i]);
+                            } else if (!HALF || (i & 1) == 0) {
                                 acc[nt][tile][i] = fmaf(SPLIT_INV, accs[nt][tile][0][i] + accs[nt][tile][SL][i], acc[nt][tile][i]);
+                            }
                 }
                 if (SPLIT) {                       // strict activations (gates.cuh), nothing shared between pairs
 #pragma unroll
@@ -450,7 +477,7 @@ __global__ void __launch_bounds__(128, (FMT == FMT_TF32 || HALF || SPLIT) ? 2 : 
                 for (int e = 0; e < NE; ++e) {
                     hst[nt][0][e] = hn[0][e];
                     hst[nt][1][e] = hn[1][e];
-                    store_state2<FMT, SPLIT>(hnext + (nt * 8 + 2 * tig + e) * F::ROW_BYTES, u0, hn[0][e], hn[1][e]);
+                    put_state(hnext, nt * 8 + 2 * tig + e, hn[0][e], hn[1][e]);
                 }
             }
             cur ^= 1;
@@ -462,7 +489,7 @@ __global__ void __launch_bounds__(128, (FMT == FMT_TF32 || HALF || SPLIT) ? 2 : 
             for (int nt = 0; nt < NT; ++nt) {
                 if (DEFER && n > 1 && gid == 0) // (the pending head of the step before it)
                     *reinterpret_cast<float2*>(yp + (warp * CH + n - 2) * C::YP_LD + nt * 8 + 2 * tig) = head_value(hpend[nt]);
-                uint32_t bfin[NP][BW];
+                uint32_t bfin[NPB][BW];
                 float ch[4];
                 load_bfrag(hb + cur * C::HB_BYTES, nt, bfin);
                 head_mma(bfin, ch);
