@@ -407,6 +407,10 @@ def test_all_12_shipped_best_checkpoints_vs_reference(mode):
                         esr = c_oracle.esr(got[0, 0], want)
                         assert esr <= 1e-4, (i, kind, sig, esr)
                     else:
-                        assert np.all(np.isfinite(got))
+                        # the checkpoint amplifies round-off on this signal (one case: _BEST #2 on the sine, where the reference's
+                        # own fp32-vs-fp64 distance is 2.6e-4): 11-bit operands are 2^13 unit round-offs coarser than fp32, the
+                        # error may grow to half of 2^13 floors (achieved 924 floors, profiles/r02_parity.json), full scale at most
+                        err = float(np.max(np.abs(got[0, 0] - want)))
+                        assert np.all(np.isfinite(got)) and err <= min(1.0, 4096.0 * floor), (i, kind, sig, err, floor)
         n += 1
     assert n == 12
