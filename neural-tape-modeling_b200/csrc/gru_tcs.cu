@@ -121,33 +121,6 @@ __device__ __forceinline__ void tmem_st2(uint32_t taddr, uint32_t r0, uint32_t r
 // ---- packed fp32 arithmetic (sm_100: add / mul / fma .f32x2 = FADD2 / FMUL2 / FFMA2) ------------------------------------
 // The epilogue is co-limited by the MUFU pipe and by ISSUE SLOTS (ncu r01: issue 68 %, XU 78 %, FMA pipe 37 %): every
 // operation on the two hidden units of a pair is the same instruction twice, so it is issued once on a register pair.
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pk(float lo, float hi)
-{
-    f32x2 r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void upk(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
-{
-    f32x2 d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-    return d;
-}
-__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b)
-{
-    f32x2 d;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
-__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b)
-{
-    f32x2 d;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
-
 // New states of the two hidden units (j, j + 1) of one stream from their accumulator values.
 //   AUG formats: ar, az are complete scaled pre-activations, an = W_hn h + b_hn.
 //   others:      ar, az, an = (gain x) W_h* h; input projection and biases are added here in fp32.
