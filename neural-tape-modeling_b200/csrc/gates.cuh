@@ -61,8 +61,10 @@ __device__ __forceinline__ void gates_rz_dn_pre(float ar, float az, float an, fl
 // wait for z's ex2 and two more multiplies), z's ex2 / rcp fill the MUFU pipe's idle slots.  5.5 MUFU per pair.
 __device__ __forceinline__ void gates_rz_dn_fast_r(const UnitConst& c, float ar, float az, float an, float x, float& z, float& dn)
 {
+    // (no clamp on the n gate's 2^s: its denominator gets its OWN reciprocal in this form, and 2^s = inf gives 1 / dn = 0, n = 1 --
+    // the limit; the clamp only matters where denominators are multiplied.  Two FMNMX less per step; measured neutral.)
     const float r = rcp_approx(1.0f + ex2_approx(ar + fmaf(c.cr_w, x, c.cr_b)));
-    dn = 1.0f + ex2_approx(fminf(fmaf(r, an + c.ch_b, fmaf(c.cn_w, x, c.cn_b)), EX2_CLAMP));
+    dn = 1.0f + ex2_approx(fmaf(r, an + c.ch_b, fmaf(c.cn_w, x, c.cn_b)));
     z = rcp_approx(1.0f + ex2_approx(az + fmaf(c.cz_w, x, c.cz_b)));
 }
 

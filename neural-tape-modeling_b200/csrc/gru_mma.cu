@@ -194,6 +194,20 @@ __global__ void __launch_bounds__(128, (FMT == FMT_TF32 || HALF || SPLIT) ? 2 : 
             }
         }
     };
+    // The same for the step loop.  Deferred-head forms (a warp alone on its SM sub-partition), f16 / bf16, rounded modes: this
+    // warp's two words of the fragment are loaded again with one LDS.64 at a per-warp address instead of being selected from the
+    // eight in registers (four SEL per step): 171.6 -> 168.1 ns/step at batch 1, cfg 3 181.7 -> 178.6.  With two CTAs per SM the
+    // same change costs 8 % (215.7 -> 232.2 ns/step: one more shared-memory access per step in front of an HMMA), so the
+    // immediate-head form keeps the selects (profiles/r02_mma_variants.txt).
+    auto head_mma_step = [&](const uint8_t* tile, int nt, const uint32_t (&bp)[NPB][BW], float (&c)[4]) {
+        if (DEFER && HK == 1 && NPB == 1 && !SPLIT) {
+            const uint2 w2 = *reinterpret_cast<const uint2*>(tile + (nt * 8 + gid) * F::ROW_BYTES + tig * 32 + warp * 8);
+            c[0] = c[1] = c[2] = c[3] = 0.0f;
+            mma_sync<FMT>(c, ahead[0], w2.x, w2.y);
+        } else {
+            head_mma(bp, c);
+        }
+    };
     // the two columns of a head tile -> the samples of streams 2tig, 2tig + 1
     auto head_value = [&](const float (&c)[4]) {
         if (PAIRCOL) return make_float2(fmaf(SPLIT_INV, c[1] + c[2], c[0]), 0.0f);
@@ -404,10 +418,10 @@ __global__ void __launch_bounds__(128, (FMT == FMT_TF32 || HALF || SPLIT) ? 2 : 
                 if (DEFER) {
                     if (tt > 1 && gid == 0)
                         *reinterpret_cast<float2*>(yp + (warp * CH + tt - 2) * C::YP_LD + nt * 8 + 2 * tig) = head_value(hpend[nt]);
-                    head_mma(breg[nt], hpend[nt]);
+                    head_mma_step(hcur, nt, breg[nt], hpend[nt]);
                 } else {
                     float ch[4];
-                    head_mma(breg[nt], ch);
+                    head_mma_step(hcur, nt, breg[nt], ch);
                     if (tt > 0 && gid == 0)
                         *reinterpret_cast<float2*>(yp + (warp * CH + tt - 1) * C::YP_LD + nt * 8 + 2 * tig) = head_value(ch);
                 }
