@@ -92,6 +92,7 @@ cudaError_t launch_gru_fp32(const GruArgs& a, int sm_count, int tune_s, int tune
 cudaError_t launch_gru_tcs(const GruArgs& a, const TcsConsts& kc, int fmt, int sm_count, int tiles, int var, cudaStream_t st);
 void fill_tcs_consts(const float* blob_host, TcsConsts* kc);
 cudaError_t launch_gru_mma(const GruArgs& a, int fmt, int n_tiles, cudaStream_t st);
+cudaError_t launch_gru_mma4(const GruArgs& a, int fmt, cudaStream_t st);   // plain GRU, f16 / bf16, four streams per CTA, 4x unrolled
 cudaError_t launch_gru_mma_rt(const GruArgs& a, int fmt, cudaStream_t st);    // resident real-time server, <= 4 streams
 void pack_tc_images(float* blob_host);   // host: fills BlobLayout::IMG_* from the fp32 part of the blob
 cudaError_t launch_delay(const float* x, long long ldx, const float* d, long long ldd, float* y, long long ldy,

@@ -16,7 +16,7 @@ from conftest import load_ckpt
 dev = "cuda:0"
 L = lib.load()
 mode = sys.argv[1] if len(sys.argv) > 1 else "f16"
-TUNES = ((4, 3), (8, 3), (8, 5), (0, 0))
+TUNES = ((4, 3), (8, 3), (0, 0))
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 with torch.inference_mode():
     m = ntm_b200.RNN(1, 64, 1, False).to(dev)
