@@ -1,5 +1,5 @@
-// Lean form of the warp-level mma.sync GRU kernel for the width BASELINE cfg 2 runs at: plain GRU, f16 / bf16 operands, FOUR
-// streams per CTA, two CTAs per SM (more than 4 and up to 8 streams per SM).
+// Lean form of the warp-level mma.sync GRU kernel for the width BASELINE cfg 2 runs at and below: plain GRU, f16 / bf16 operands or
+// the strict f16x3 mode, FOUR streams per CTA, up to two CTAs per SM (up to 8 streams per SM).
 //
 // Arithmetic, fragment layout and results are those of gru_mma.cu's 4-stream form, bit for bit (`self.GRU(x, self.hidden)` +
 // `self.output(x)` of RNN.forward, code/model.py:81-82; torch rnn.py:1221-1224): warp w owns hidden units [16w, 16w+16) as the
@@ -16,7 +16,7 @@
 //     step), which also keeps the head accumulators away from their HMMA (the "deferred head" effect without its burst);
 //   * the two state tiles alternate at compile time (no tile address arithmetic, no toggle), the loop counter and its compare
 //     are paid once per four steps.
-// DiffDelRNN, the strict mode, tf32, the real-time server and every other width stay in gru_mma.cu.
+// DiffDelRNN, tf32, the real-time server and every other width stay in gru_mma.cu.
 #include <type_traits>
 
 #include "gates.cuh"
@@ -53,10 +53,14 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 
 // (The head's fragment words are selected from the eight in registers: loading them again with an LDS.64, which helps the
 // general kernel's deferred-head form, measured slower here at every width: 167.3 vs 162.0 ns/step at batch 1.)
-template <int FMT>
+// STRICT: the fp32-grade f16x3 mode in its pair-column layout (gru_mma.cu, PAIRCOL): a stream's even column carries h_hi, the odd
+// column next to it the scaled residual h_lo'; W_hi [h_hi | h_lo'] and W_lo' h_hi -- two MMAs per product --, Newton-refined
+// reciprocals (gates_strict).
+template <int FMT, bool STRICT>
 __global__ void __launch_bounds__(128, 2) gru_mma4_kernel(const GruArgs a)
 {
-    static_assert(FMT == FMT_F16 || FMT == FMT_BF16, "16-bit operand formats");
+    static_assert(FMT == FMT_F16 || (FMT == FMT_BF16 && !STRICT), "16-bit operand formats; the strict form is f16");
+    constexpr int NP = STRICT ? 2 : 1;
     using C = Mma4Cfg<FMT>;
     using F = Frag<FMT, false>;
     constexpr int SC = C::SC, CH = C::CH, NK = F::NK, YLD = C::YLD;
@@ -73,7 +77,7 @@ __global__ void __launch_bounds__(128, 2) gru_mma4_kernel(const GruArgs a)
     const float* __restrict__ blob = a.blob;
 
     // ---- W_hh fragments -> registers (layout and K permutation of gru_mma.cu) ---------------------------------------------
-    uint32_t areg[3][NK][4];
+    uint32_t areg[NP][3][NK][4];
     {
         const float sc[3] = {-LOG2E_F4, -LOG2E_F4, 2.0f * LOG2E_F4};
 #pragma unroll
@@ -86,7 +90,12 @@ __global__ void __launch_bounds__(128, 2) gru_mma4_kernel(const GruArgs a)
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const float* row = (i & 1) ? hi : lo;
-                    areg[tile][ks][i] = pack2<FMT>(sc[tile] * row[k + 2 * (i >> 1)], sc[tile] * row[k + 2 * (i >> 1) + 1]);
+                    const float w0 = sc[tile] * row[k + 2 * (i >> 1)], w1 = sc[tile] * row[k + 2 * (i >> 1) + 1];
+                    areg[0][tile][ks][i] = pack2<FMT>(w0, w1);
+                    if (STRICT) {
+                        const float2 wh = __half22float2(__floats2half2_rn(w0, w1));
+                        areg[NP - 1][tile][ks][i] = pack2<FMT>((w0 - wh.x) * SPLIT_SCALE, (w1 - wh.y) * SPLIT_SCALE);
+                    }
                 }
             }
         }
@@ -101,8 +110,9 @@ __global__ void __launch_bounds__(128, 2) gru_mma4_kernel(const GruArgs a)
             w[i] = gid == 0 ? blob[BlobLayout::W_OUT + tig * 16 + 4 * warp + i] : 0.0f;
             hi[i] = FMT == FMT_BF16 ? __bfloat162float(__float2bfloat16_rn(w[i])) : __half2float(__float2half_rn(w[i]));
         }
-        ahead[0] = pack2<FMT>(hi[0], hi[1]); ahead[1] = pack2<FMT>(w[0] - hi[0], w[1] - hi[1]);
-        ahead[2] = pack2<FMT>(hi[2], hi[3]); ahead[3] = pack2<FMT>(w[2] - hi[2], w[3] - hi[3]);
+        const float rs = STRICT ? SPLIT_SCALE : 1.0f;      // (strict: row 8 = w_lo', scaled like the state residual)
+        ahead[0] = pack2<FMT>(hi[0], hi[1]); ahead[1] = pack2<FMT>((w[0] - hi[0]) * rs, (w[1] - hi[1]) * rs);
+        ahead[2] = pack2<FMT>(hi[2], hi[3]); ahead[3] = pack2<FMT>((w[2] - hi[2]) * rs, (w[3] - hi[3]) * rs);
     }
 
     // x staging: [buf][stream][CH], time contiguous.  16-byte copies when every row chunk is 16-byte aligned.
@@ -129,12 +139,23 @@ __global__ void __launch_bounds__(128, 2) gru_mma4_kernel(const GruArgs a)
     // ---- initial state: fp32 in registers, rounded copy into state tile 0; the odd (dead) columns of both tiles stay zero ----
     float hst[2] = {0.0f, 0.0f};
     if (tig < ns && a.h_in) { hst[0] = a.h_in[(b0 + tig) * 64 + u0]; hst[1] = a.h_in[(b0 + tig) * 64 + u1]; }
+    auto state_words = [&](float v0, float v1, uint32_t& whi, uint32_t& wlo) {
+        whi = pack2<FMT>(v0, v1);
+        wlo = 0u;
+        if (STRICT) {
+            const float2 hf = __half22float2(__floats2half2_rn(v0, v1));
+            wlo = pack2<FMT>((v0 - hf.x) * SPLIT_SCALE, (v1 - hf.y) * SPLIT_SCALE);
+        }
+    };
+    {
+        uint32_t whi, wlo;
+        state_words(hst[0], hst[1], whi, wlo);
 #pragma unroll
-    for (int t = 0; t < 2; ++t)
+        for (int t = 0; t < 2; ++t)
 #pragma unroll
-        for (int e = 0; e < 2; ++e)
-            *reinterpret_cast<uint32_t*>(hb + t * C::TILE_BYTES + (2 * tig + e) * F::ROW_BYTES + u0 * 2) =
-                (t == 0 && e == 0) ? pack2<FMT>(hst[0], hst[1]) : 0u;
+            for (int e = 0; e < 2; ++e)
+                *reinterpret_cast<uint32_t*>(hb + t * C::TILE_BYTES + (2 * tig + e) * F::ROW_BYTES + u0 * 2) = t ? 0u : (e ? wlo : whi);
+    }
 
     // per-thread addresses: B fragments of tile t, state word of tile t, x row, head-partial row
     const uint8_t* const frag[2] = {hb + gid * F::ROW_BYTES + tig * 32, hb + C::TILE_BYTES + gid * F::ROW_BYTES + tig * 32};
@@ -151,31 +172,56 @@ __global__ void __launch_bounds__(128, 2) gru_mma4_kernel(const GruArgs a)
             const uint4 v1 = *reinterpret_cast<const uint4*>(frag[P] + 16);
             b[0] = v0.x; b[1] = v0.y; b[2] = v0.z; b[3] = v0.w; b[4] = v1.x; b[5] = v1.y; b[6] = v1.z; b[7] = v1.w;
         }
-        float acc[3][4], ch[4];
+        float acc[3][4], accl[STRICT ? 3 : 1][4], ch[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) acc[0][i] = acc[1][i] = acc[2][i] = ch[i] = 0.0f;
+        for (int i = 0; i < 4; ++i) {
+            acc[0][i] = acc[1][i] = acc[2][i] = ch[i] = 0.0f;
+            if (STRICT) accl[0][i] = accl[STRICT ? 1 : 0][i] = accl[STRICT ? 2 : 0][i] = 0.0f;
+        }
+        auto tile_mma = [&](int tile, int ks) {
+            mma_sync<FMT>(acc[tile], areg[0][tile][ks], b[2 * ks], b[2 * ks + 1]);
+            if (STRICT) mma_sync<FMT>(accl[STRICT ? tile : 0], areg[NP - 1][tile][ks], b[2 * ks], b[2 * ks + 1]);
+        };
         // critical path first: r -> n -> h' is the step's dependent chain; r and n alternate, z follows
 #pragma unroll
         for (int ks = 0; ks < NK; ++ks) {
-            mma_sync<FMT>(acc[0], areg[0][ks], b[2 * ks], b[2 * ks + 1]);
-            mma_sync<FMT>(acc[2], areg[2][ks], b[2 * ks], b[2 * ks + 1]);
+            tile_mma(0, ks);
+            tile_mma(2, ks);
         }
 #pragma unroll
-        for (int ks = 0; ks < NK; ++ks) mma_sync<FMT>(acc[1], areg[1][ks], b[2 * ks], b[2 * ks + 1]);
+        for (int ks = 0; ks < NK; ++ks) tile_mma(1, ks);
         {
             const uint32_t h0 = (warp & 2) ? ((warp & 1) ? b[6] : b[4]) : ((warp & 1) ? b[2] : b[0]);
             const uint32_t h1 = (warp & 2) ? ((warp & 1) ? b[7] : b[5]) : ((warp & 1) ? b[3] : b[1]);
             mma_sync<FMT>(ch, ahead, h0, h1);
         }
+        if (STRICT) {                          // W h = W_hi h_hi + 2^-11 (W_hi h_lo' [odd column] + W_lo' h_hi)
+#pragma unroll
+            for (int tile = 0; tile < 3; ++tile)
+#pragma unroll
+                for (int i = 0; i < 4; i += 2)
+                    acc[tile][i] = fmaf(SPLIT_INV, acc[tile][i + 1] + accl[STRICT ? tile : 0][i], acc[tile][i]);
+        }
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
-            float z, dn;
-            gates_rz_dn_fast_r(uc[u], acc[0][2 * u], acc[1][2 * u], acc[2][2 * u], xx, z, dn);
-            hst[u] = gates_blend1_late(z, dn, hst[u]);
+            if (STRICT) {
+                const float pr = acc[0][2 * u] + fmaf(uc[u].cr_w, xx, uc[u].cr_b);
+                const float pz = acc[1][2 * u] + fmaf(uc[u].cz_w, xx, uc[u].cz_b);
+                hst[u] = gates_strict(pr, pz, acc[2][2 * u] + uc[u].ch_b, fmaf(uc[u].cn_w, xx, uc[u].cn_b), hst[u]);
+            } else {
+                float z, dn;
+                gates_rz_dn_fast_r(uc[u], acc[0][2 * u], acc[1][2 * u], acc[2][2 * u], xx, z, dn);
+                hst[u] = gates_blend1_late(z, dn, hst[u]);
+            }
         }
-        *reinterpret_cast<uint32_t*>(word[P ^ 1]) = pack2<FMT>(hst[0], hst[1]);
+        {
+            uint32_t whi, wlo;
+            state_words(hst[0], hst[1], whi, wlo);
+            *reinterpret_cast<uint32_t*>(word[P ^ 1]) = whi;
+            if (STRICT) *reinterpret_cast<uint32_t*>(word[P ^ 1] + F::ROW_BYTES) = wlo;
+        }
         __syncthreads();                       // next state tile published; all reads of the old one are done
-        return ch[0] + ch[2];
+        return STRICT ? fmaf(SPLIT_INV, ch[1] + ch[2], ch[0]) : ch[0] + ch[2];
     };
     using T0 = std::integral_constant<int, 0>;
     using T1 = std::integral_constant<int, 1>;
@@ -215,7 +261,7 @@ __global__ void __launch_bounds__(128, 2) gru_mma4_kernel(const GruArgs a)
             const uint4 v = *reinterpret_cast<const uint4*>(src);
             float ch[4] = {0.0f, 0.0f, 0.0f, 0.0f};
             mma_sync<FMT>(ch, ahead, (warp & 1) ? v.z : v.x, (warp & 1) ? v.w : v.y);
-            if (gid == 0) yrow[n] = ch[0] + ch[2];
+            if (gid == 0) yrow[n] = STRICT ? fmaf(SPLIT_INV, ch[1] + ch[2], ch[0]) : ch[0] + ch[2];
         }
         __syncthreads();
         // ---- flush the chunk: y = sum of the four warps' partials + bias (+ x) ----------------------------------------
@@ -232,22 +278,23 @@ __global__ void __launch_bounds__(128, 2) gru_mma4_kernel(const GruArgs a)
     if (tig < ns) { a.h_out[(b0 + tig) * 64 + u0] = hst[0]; a.h_out[(b0 + tig) * 64 + u1] = hst[1]; }
 }
 
-template <int FMT>
+template <int FMT, bool STRICT = false>
 cudaError_t launch_mma4_one(const GruArgs& a, cudaStream_t st)
 {
     using C = Mma4Cfg<FMT>;
-    gru_mma4_kernel<FMT><<<(unsigned)((a.B + C::SC - 1) / C::SC), 128, C::SMEM_BYTES, st>>>(a);
+    gru_mma4_kernel<FMT, STRICT><<<(unsigned)((a.B + C::SC - 1) / C::SC), 128, C::SMEM_BYTES, st>>>(a);
     ++g_launches;
     return cudaGetLastError();
 }
 
 }  // namespace
 
-// Plain GRU batches, f16 / bf16 operands, four streams per CTA.
+// Plain GRU batches, f16 / bf16 operands or the strict f16x3 mode, four streams per CTA.
 cudaError_t launch_gru_mma4(const GruArgs& a, int fmt, cudaStream_t st)
 {
     if (a.B <= 0 || a.T <= 0) return cudaSuccess;
-    if (a.d != nullptr || (fmt != FMT_F16 && fmt != FMT_BF16)) return cudaErrorInvalidValue;
+    if (a.d != nullptr || (fmt != FMT_F16 && fmt != FMT_BF16 && fmt != FMT_F16X3)) return cudaErrorInvalidValue;
+    if (fmt == FMT_F16X3) return launch_mma4_one<FMT_F16, true>(a, st);
     return fmt == FMT_BF16 ? launch_mma4_one<FMT_BF16>(a, st) : launch_mma4_one<FMT_F16>(a, st);
 }
 

@@ -16,7 +16,7 @@ dev = "cuda:0"
 L = lib.load()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 with torch.inference_mode():
-    for mode in ("f16", "bf16"):
+    for mode in ("f16", "bf16", "f16x3"):
         for skip in (False, True):
             m = ntm_b200.RNN(1, 64, 1, skip).to(dev)
             m.load_state_dict(load_ckpt("cfg2"))
@@ -37,20 +37,21 @@ with torch.inference_mode():
                 print(f"{mode} skip={skip} B={B} T={T} off={off}: identical={same} finite={bool(torch.isfinite(outs[1][0]).all())}", flush=True)
     m = ntm_b200.RNN(1, 64, 1, False).to(dev)
     m.load_state_dict(load_ckpt("cfg2"))
-    m.mode = "f16"
     m.initialize_hidden(); m.warm_start()
     hw = m.hidden.clone()
-    for B, T in ((1, 100000), (592, 48000), (597, 48000), (1024, 48000), (1184, 48000)):
-        x = signals.stream_batch_device(B, T, dev, dur=10.0).reshape(B, 1, T)
-        row = []
-        for tune in ((4, 3), (4, 6), (0, 0)):
-            L.ntm_set_tuning(*tune)
-            m.hidden = hw.expand(1, B, 64).contiguous(); m(x[:, :, :1000])
-            best = 1e9
-            for _ in range(3):
-                m.hidden = hw.expand(1, B, 64).contiguous()
-                e0.record(); y = m(x); e1.record(); torch.cuda.synchronize()
-                best = min(best, e0.elapsed_time(e1))
-            row.append(f"{tune} {best*1e6/T:6.1f} ns/step")
-        print(f"f16 B={B}: " + " | ".join(row), flush=True)
+    for smode in ("f16", "f16x3"):
+        m.mode = smode
+        for B, T in ((1, 100000), (592, 48000), (597, 48000), (1024, 48000), (1184, 48000)):
+            x = signals.stream_batch_device(B, T, dev, dur=10.0).reshape(B, 1, T)
+            row = []
+            for tune in ((4, 3), (4, 6), (0, 0)):
+                L.ntm_set_tuning(*tune)
+                m.hidden = hw.expand(1, B, 64).contiguous(); m(x[:, :, :1000])
+                best = 1e9
+                for _ in range(3):
+                    m.hidden = hw.expand(1, B, 64).contiguous()
+                    e0.record(); y = m(x); e1.record(); torch.cuda.synchronize()
+                    best = min(best, e0.elapsed_time(e1))
+                row.append(f"{tune} {best*1e6/T:6.1f} ns/step")
+            print(f"{smode} B={B}: " + " | ".join(row), flush=True)
 L.ntm_set_tuning(0, 0)
