@@ -123,9 +123,10 @@ int run_gru(Handle* hd, int mode, const ntm::GruArgs& a, cudaStream_t st)
             int nt;
             if (tune.s > 0 && tg == 3) nt = tune.s / 8;
             else nt = a.B <= 8ll * hd->sm_count ? 0 : 1;
-            // four streams per CTA, plain GRU, 16-bit operands (cfg 2's width and below): the lean form of gru_mma4.cu (same
-            // results, bit for bit: 204 vs 215 ns/step at 1024 streams, 162 vs 168 at batch 1); forced with tuning (4, 6)
-            const bool lean_ok = !a.d && (fmt == 0 || fmt == 1 || fmt == 3);
+            // four streams per CTA, 16-bit operands or the strict mode (cfg 2's width and below, GRU and DiffDelGRU): the lean
+            // form of gru_mma4.cu (same results, bit for bit: 204 vs 215 ns/step at 1024 streams, 162 vs 168 at batch 1);
+            // forced with tuning (4, 6); (4, 3) keeps the general kernel
+            const bool lean_ok = fmt == 0 || fmt == 1 || fmt == 3;
             const bool lean = lean_ok && (tg == 6 || (tg == 0 && nt == 0));
             if (lean) CU(ntm::launch_gru_mma4(a, fmt, st));
             else CU(ntm::launch_gru_mma(a, fmt, nt, st));

@@ -1,8 +1,9 @@
-// Lean form of the warp-level mma.sync GRU kernel for the width BASELINE cfg 2 runs at and below: plain GRU, f16 / bf16 operands or
-// the strict f16x3 mode, FOUR streams per CTA, up to two CTAs per SM (up to 8 streams per SM).
+// Lean form of the warp-level mma.sync GRU kernel for the widths BASELINE cfg 2, 3 and 5 run at: GRU and DiffDelGRU, f16 / bf16
+// operands or the strict f16x3 mode, FOUR streams per CTA, up to two CTAs per SM (up to 8 streams per SM).
 //
 // Arithmetic, fragment layout and results are those of gru_mma.cu's 4-stream form, bit for bit (`self.GRU(x, self.hidden)` +
-// `self.output(x)` of RNN.forward, code/model.py:81-82; torch rnn.py:1221-1224): warp w owns hidden units [16w, 16w+16) as the
+// `self.output(x)` of RNN.forward / DiffDelRNN.forward, code/model.py:81-82, :412-413, the delay read of :422; torch
+// rnn.py:1221-1224): warp w owns hidden units [16w, 16w+16) as the
 // three m16 tiles r, z, n; W_hh fragments in registers; the streams sit in the even columns of the n8 tile; r and n MMAs
 // interleaved, z behind; own reciprocals; late blend; head as a fourth tile with K split over the warps.
 //
@@ -16,7 +17,7 @@
 //     step), which also keeps the head accumulators away from their HMMA (the "deferred head" effect without its burst);
 //   * the two state tiles alternate at compile time (no tile address arithmetic, no toggle), the loop counter and its compare
 //     are paid once per four steps.
-// DiffDelRNN, tf32, the real-time server and every other width stay in gru_mma.cu.
+// tf32, the real-time server and every other width stay in gru_mma.cu.
 #include <type_traits>
 
 #include "gates.cuh"
@@ -42,7 +43,8 @@ struct Mma4Cfg {
     static constexpr int OFF_HB = 0;                                         // [2][8][ROW_BYTES]
     static constexpr int OFF_XS = (2 * TILE_BYTES + 127) / 128 * 128;        // [2][SC][CH] floats
     static constexpr int OFF_YP = OFF_XS + 2 * SC * CH * 4;                  // [4 warps][SC][YLD] floats
-    static constexpr int SMEM_BYTES = OFF_YP + 4 * SC * YLD * 4;
+    static constexpr int OFF_DS = OFF_YP + 4 * SC * YLD * 4;                 // [2][SC][CH] delay trajectory (DiffDelRNN)
+    static constexpr int SMEM_BYTES = OFF_DS + 2 * SC * CH * 4;              // + the pre_d ring [SC][ring_len], sized at launch
 };
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
@@ -68,6 +70,8 @@ __global__ void __launch_bounds__(128, 2) gru_mma4_kernel(const GruArgs a)
     uint8_t* const hb = smem + C::OFF_HB;
     float* const xs = reinterpret_cast<float*>(smem + C::OFF_XS);
     float* const yp = reinterpret_cast<float*>(smem + C::OFF_YP);
+    float* const ds = reinterpret_cast<float*>(smem + C::OFF_DS);
+    float* const ring = reinterpret_cast<float*>(smem + C::SMEM_BYTES);      // [SC][a.ring_len] when a.ring_len > 0
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int gid = lane >> 2, tig = lane & 3;        // tig = this thread's stream
@@ -135,6 +139,32 @@ __global__ void __launch_bounds__(128, 2) gru_mma4_kernel(const GruArgs a)
         }
         cp_async_commit();
     };
+
+    // DiffDelRNN (code/model.py:393-424): the head output is pre_d, y is the fractional-delay read of it (delay_read,
+    // ntm_common.cuh: bit-exact against the reference given the same pre_d), fused at the chunk flush.  The taps come from an
+    // on-chip ring of the last ring_len >= D + CH samples of pre_d per stream (carried history included) when it fits, from the
+    // chunk just written through L2 otherwise; the delay trajectory is staged like x.
+    const bool delay = a.d != nullptr;
+    float* __restrict__ head_out = delay ? a.pre : a.y;
+    const long long ldo = delay ? a.ldp : a.ldy;
+    const int rmask = a.ring_len - 1;
+    const bool use_ring = delay && !a.warmup && a.ring_len > 0;
+    auto load_d = [&](int buf, long long t0) {
+        const int n = (int)((a.T - t0) < (long long)CH ? (a.T - t0) : (long long)CH);
+        float* dstb = ds + buf * SC * CH;
+        for (int idx = tid; idx < SC * CH; idx += 128) {
+            const int s = idx / CH, tt = idx % CH;
+            if (s < ns && tt < n) cp_async4(dstb + idx, a.d + (b0 + s) * a.ldd + t0 + tt);
+        }
+        cp_async_commit();
+    };
+    if (use_ring) {                                          // carried history -> ring positions -D .. -1
+        for (long long idx = tid; idx < (long long)ns * a.D; idx += 128) {
+            const int s = (int)(idx / a.D);
+            const int i = (int)(idx % a.D);
+            ring[s * a.ring_len + ((i - a.D) & rmask)] = a.hist_in[(b0 + s) * (long long)a.D + i];
+        }
+    }
 
     // ---- initial state: fp32 in registers, rounded copy into state tile 0; the odd (dead) columns of both tiles stay zero ----
     float hst[2] = {0.0f, 0.0f};
@@ -229,6 +259,7 @@ __global__ void __launch_bounds__(128, 2) gru_mma4_kernel(const GruArgs a)
     const long long nchunks = (a.T + CH - 1) / CH;
     int cur = 0;                               // tile holding the current state at a chunk boundary (0 unless a chunk was odd)
     load_x(0, 0);
+    if (use_ring) load_d(0, 0);
     for (long long c = 0; c < nchunks; ++c) {
         const long long t0 = c * CH;
         const int n = (int)((a.T - t0) < (long long)CH ? (a.T - t0) : (long long)CH);
@@ -236,7 +267,10 @@ __global__ void __launch_bounds__(128, 2) gru_mma4_kernel(const GruArgs a)
         const float* xcur = xs + xb * SC * CH;
         cp_async_wait_all();
         __syncthreads();                       // xs[xb] landed; state tile `cur` complete; previous flush done
-        if (c + 1 < nchunks) load_x(xb ^ 1, t0 + CH);
+        if (c + 1 < nchunks) {
+            load_x(xb ^ 1, t0 + CH);
+            if (use_ring) load_d(xb ^ 1, t0 + CH);
+        }
 
         const float* xrow = xcur + tig * CH;
         int tt = 0;
@@ -264,36 +298,90 @@ __global__ void __launch_bounds__(128, 2) gru_mma4_kernel(const GruArgs a)
             if (gid == 0) yrow[n] = STRICT ? fmaf(SPLIT_INV, ch[1] + ch[2], ch[0]) : ch[0] + ch[2];
         }
         __syncthreads();
-        // ---- flush the chunk: y = sum of the four warps' partials + bias (+ x) ----------------------------------------
+        // ---- flush the chunk: head output = sum of the four warps' partials + bias (+ x) ------------------------------
         for (int idx = tid; idx < SC * CH; idx += 128) {
             const int s = idx / CH, t = idx % CH;
             if (s < ns && t < n) {
                 float v = yp[s * YLD + t + 1] + yp[(SC + s) * YLD + t + 1] + yp[(2 * SC + s) * YLD + t + 1] +
                           yp[(3 * SC + s) * YLD + t + 1] + bo;
                 if (a.skip) v += xcur[s * CH + t];
-                a.y[(b0 + s) * a.ldy + t0 + t] = v;
+                head_out[(b0 + s) * ldo + t0 + t] = v;
+                if (delay && a.warmup) a.y[(b0 + s) * a.ldy + t0 + t] = v;
+                if (use_ring) ring[s * a.ring_len + ((int)(t0 + t) & rmask)] = v;
+            }
+        }
+        if (use_ring) {
+            __syncthreads();
+            const float* dcur = ds + xb * SC * CH;
+            for (int idx = tid; idx < SC * CH; idx += 128) {
+                const int s = idx / CH, t = idx % CH;
+                if (s < ns && t < n) {
+                    const long long tg = t0 + t;
+                    const float* rrow = ring + s * a.ring_len;
+                    a.y[(b0 + s) * a.ldy + tg] = delay_read(dcur[idx], tg, a.D, [&](long long i) { return rrow[(int)i & rmask]; });
+                }
+            }
+        } else if (delay && !a.warmup) {
+            __syncthreads();                   // this chunk's pre_d is visible CTA-wide (L2 reads below)
+            for (int idx = tid; idx < SC * CH; idx += 128) {
+                const int s = idx / CH, t = idx % CH;
+                if (s < ns && t < n) {
+                    const long long tg = t0 + t;
+                    const float* prow = a.pre + (b0 + s) * a.ldp;
+                    const float* hrow = a.hist_in + (b0 + s) * (long long)a.D;
+                    a.y[(b0 + s) * a.ldy + tg] = delay_read(a.d[(b0 + s) * a.ldd + tg], tg, a.D,
+                                                            [&](long long i) { return i >= 0 ? __ldcg(prow + i) : hrow[a.D + i]; });
+                }
             }
         }
     }
     if (tig < ns) { a.h_out[(b0 + tig) * 64 + u0] = hst[0]; a.h_out[(b0 + tig) * 64 + u1] = hst[1]; }
+    if (delay) {                               // rolled delay history (code/model.py:314-315)
+        __syncthreads();
+        for (long long idx = tid; idx < (long long)ns * a.D; idx += 128) {
+            const int s = (int)(idx / a.D);
+            const long long i = idx % a.D;
+            const long long src = a.T - a.D + i;
+            a.hist_out[(b0 + s) * (long long)a.D + i] =
+                src >= 0 ? __ldcg(a.pre + (b0 + s) * a.ldp + src) : a.hist_in[(b0 + s) * (long long)a.D + a.D + src];
+        }
+    }
 }
 
 template <int FMT, bool STRICT = false>
 cudaError_t launch_mma4_one(const GruArgs& a, cudaStream_t st)
 {
     using C = Mma4Cfg<FMT>;
-    gru_mma4_kernel<FMT, STRICT><<<(unsigned)((a.B + C::SC - 1) / C::SC), 128, C::SMEM_BYTES, st>>>(a);
+    static OncePerDevice once;
+    cudaError_t e = once.run([] {
+        return cudaFuncSetAttribute(gru_mma4_kernel<FMT, STRICT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES + 48 * 1024);
+    });
+    if (e != cudaSuccess) return e;
+    // DiffDelRNN: keep the last D + CH samples of pre_d per stream on chip if they fit (<= 48 KB of ring per CTA); longer
+    // histories read their taps back through L2
+    GruArgs b = a;
+    b.ring_len = 0;
+    int smem_bytes = C::SMEM_BYTES;
+    if (a.d != nullptr && !a.warmup) {
+        long long rl = 64;
+        while (rl < (long long)a.D + C::CH + 1) rl *= 2;
+        if (rl * C::SC * 4 <= 48 * 1024) {
+            b.ring_len = (int)rl;
+            smem_bytes += (int)(rl * C::SC * 4);
+        }
+    }
+    gru_mma4_kernel<FMT, STRICT><<<(unsigned)((a.B + C::SC - 1) / C::SC), 128, smem_bytes, st>>>(b);
     ++g_launches;
     return cudaGetLastError();
 }
 
 }  // namespace
 
-// Plain GRU batches, f16 / bf16 operands or the strict f16x3 mode, four streams per CTA.
+// GRU and DiffDelGRU batches, f16 / bf16 operands or the strict f16x3 mode, four streams per CTA.
 cudaError_t launch_gru_mma4(const GruArgs& a, int fmt, cudaStream_t st)
 {
     if (a.B <= 0 || a.T <= 0) return cudaSuccess;
-    if (a.d != nullptr || (fmt != FMT_F16 && fmt != FMT_BF16 && fmt != FMT_F16X3)) return cudaErrorInvalidValue;
+    if (fmt != FMT_F16 && fmt != FMT_BF16 && fmt != FMT_F16X3) return cudaErrorInvalidValue;
     if (fmt == FMT_F16X3) return launch_mma4_one<FMT_F16, true>(a, st);
     return fmt == FMT_BF16 ? launch_mma4_one<FMT_BF16>(a, st) : launch_mma4_one<FMT_F16>(a, st);
 }
