@@ -60,7 +60,8 @@ extern "C" {
 #define NTM_Q_MODE_MASK      3   /* bit m set <=> mode m is implemented */
 #define NTM_Q_KERNEL_LAUNCHES 4  /* number of engine kernels launched by this process so far */
 #define NTM_Q_LAST_KERNEL    5   /* recurrent kernel of the process's last launch: 0 fp32 CUDA-core, 1 warp-level
-                                    mma.sync, 3 stream-major tcgen05 (per handle: ntm_handle_last_kernel) */
+                                    mma.sync (general form), 3 stream-major tcgen05, 4 warp-level mma.sync, lean 4-stream
+                                    form (gru_mma4_kernel) (per handle: ntm_handle_last_kernel) */
 
 int         ntm_query(int what);
 const char* ntm_strerror(int code);

@@ -130,7 +130,7 @@ int run_gru(Handle* hd, int mode, const ntm::GruArgs& a, cudaStream_t st)
             const bool lean = lean_ok && (tg == 6 || (tg == 0 && nt == 0));
             if (lean) CU(ntm::launch_gru_mma4(a, fmt, st));
             else CU(ntm::launch_gru_mma(a, fmt, nt, st));
-            kernel = 1;
+            kernel = lean ? 4 : 1;
         }
     }
     hd->last_kernel.store(kernel, std::memory_order_relaxed);

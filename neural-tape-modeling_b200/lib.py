@@ -16,7 +16,8 @@ MODES = {"fp32": MODE_FP32, "tf32": MODE_TF32, "bf16": MODE_BF16, "f16x3": MODE_
          "tf32x3": MODE_F16X3, "f16": MODE_F16}
 Q_VERSION, Q_DEVICE_COUNT, Q_SM_COUNT, Q_MODE_MASK, Q_KERNEL_LAUNCHES, Q_LAST_KERNEL = 0, 1, 2, 3, 4, 5
 KERNEL_NAMES = {0: "gru_fp32_kernel (CUDA-core FFMA)", 1: "gru_mma_kernel (warp-level mma.sync)",
-                3: "gru_tcs_kernel (tcgen05 + TMEM, stream-major)"}
+                3: "gru_tcs_kernel (tcgen05 + TMEM, stream-major)",
+                4: "gru_mma4_kernel (warp-level mma.sync, lean 4-stream form)"}
 E_DELAY = -5
 E_CLOSED = -7
 

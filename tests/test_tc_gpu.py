@@ -270,7 +270,7 @@ def test_full_size_cfg2_properties():
     with torch.inference_mode():
         y = m.predict(x)
         h_full = m.hidden.clone()
-        assert lib.query(lib.Q_LAST_KERNEL) == 1
+        assert lib.query(lib.Q_LAST_KERNEL) == 4       # cfg 2's width: the lean 4-stream mma.sync form
         assert bool(torch.isfinite(y[:, :, ::97]).all()) and bool(torch.isfinite(y[:, :, -4096:]).all())
         y1 = m.predict(x[:, :, :FS])
         assert torch.equal(y1, y[:, :, :FS])
