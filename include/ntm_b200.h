@@ -71,7 +71,11 @@ int         ntm_last_cuda_error(void);
  * Pack one model's parameters (HOST pointers, PyTorch layouts, gate row order r,z,n) into an engine-owned
  * device blob on `device`.   Replaces: RNN.__init__/load_state_dict parameter ownership, code/model.py:44-45
  * (b_out != NULL) and DiffDelRNN, code/model.py:364-365 (b_out == NULL).
- *   w_ih (3H,1)  w_hh (3H,H)  b_ih (3H)  b_hh (3H)  w_out (1,H)  b_out (1) or NULL.   H must be 64.
+ *   w_ih (3H,1)  w_hh (3H,H)  b_ih (3H)  b_hh (3H)  w_out (1,H)  b_out (1) or NULL.   1 <= H <= 64 (NTM_EUNSUPPORTED beyond).
+ * The engine's state is 64 units wide whatever H is: every `h` / `h_in` / `h_out` of this header is B x 64 floats.  A model
+ * with H < 64 (code/train.py:50 defaults to 16, scripts/sbatch-train.sh:15 trains 32) is embedded with zero weights for the
+ * units H .. 63; their state stays 0 and never reaches a real unit or the output, so the result is the H-unit GRU's exactly.
+ * Callers keep columns H .. 63 of the state zero (the Python classes pad / cut `self.hidden`).
  */
 int  ntm_gru_prepare(const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
                      const float* w_out, const float* b_out, int H, int device, void** handle);

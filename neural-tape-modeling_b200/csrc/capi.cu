@@ -124,10 +124,13 @@ int run_gru(Handle* hd, int mode, const ntm::GruArgs& a, cudaStream_t st)
             if (tune.s > 0 && tg == 3) nt = tune.s / 8;
             else nt = a.B <= 8ll * hd->sm_count ? 0 : 1;
             // four streams per CTA, 16-bit operands or the strict mode (cfg 2's width and below, GRU and DiffDelGRU): the lean
-            // form of gru_mma4.cu (same results, bit for bit: 204 vs 215 ns/step at 1024 streams, 162 vs 168 at batch 1);
+            // form of gru_mma4.cu (same results, bit for bit: 194.5 vs 215 ns/step at 1024 streams, 162 vs 168 at batch 1);
             // forced with tuning (4, 6); (4, 3) keeps the general kernel
+            // (the strict form only while every CTA has an SM of its own: with two CTAs per SM the general kernel's 4-stream
+            // form is faster, 361.7 vs 366.8 ns/step at 1024 streams)
             const bool lean_ok = fmt == 0 || fmt == 1 || fmt == 3;
-            const bool lean = lean_ok && (tg == 6 || (tg == 0 && nt == 0));
+            const bool lean_auto = nt == 0 && (fmt != 3 || a.B <= 4ll * hd->sm_count);
+            const bool lean = lean_ok && (tg == 6 || (tg == 0 && lean_auto));
             if (lean) CU(ntm::launch_gru_mma4(a, fmt, st));
             else CU(ntm::launch_gru_mma(a, fmt, nt, st));
             kernel = lean ? 4 : 1;
@@ -341,7 +344,7 @@ int ntm_gru_prepare(const float* w_ih, const float* w_hh, const float* b_ih, con
     if (!handle) return NTM_EINVAL;
     *handle = nullptr;
     if (!w_ih || !w_hh || !b_ih || !b_hh || !w_out) return NTM_EINVAL;
-    if (H != ntm::H64) return NTM_EUNSUPPORTED;
+    if (H < 1 || H > ntm::H64) return NTM_EUNSUPPORTED;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return NTM_ENODEVICE; }
     if (device < 0 || device >= ndev) return NTM_EINVAL;
@@ -355,11 +358,20 @@ int ntm_gru_prepare(const float* w_ih, const float* w_hh, const float* b_ih, con
     float* host = new (std::nothrow) float[L::TOTAL];
     if (!host) return NTM_ENOMEM;
     memset(host, 0, sizeof(float) * L::TOTAL);
-    memcpy(host + L::W_HH, w_hh, sizeof(float) * ntm::G192 * ntm::H64);
-    memcpy(host + L::W_IH, w_ih, sizeof(float) * ntm::G192);
-    memcpy(host + L::B_IH, b_ih, sizeof(float) * ntm::G192);
-    memcpy(host + L::B_HH, b_hh, sizeof(float) * ntm::G192);
-    memcpy(host + L::W_OUT, w_out, sizeof(float) * ntm::H64);
+    // PyTorch layout, gate-major (r, z, n), H units per gate.  H < 64: the model is embedded in the 64-unit engine -- unit u of
+    // gate g goes to row 64 g + u, the other rows and columns stay zero.  A padded unit has r = z = 1/2, n = tanh(0) = 0 and
+    // therefore keeps the state 0 it starts from; its column of W_hh and its head weight are zero, so no real unit or output
+    // sample depends on it: the H-unit GRU of code/model.py:44-45, term for term.
+    for (int g3 = 0; g3 < 3; ++g3) {
+        for (int u = 0; u < H; ++u) {
+            const int src = g3 * H + u, dst = g3 * ntm::H64 + u;
+            memcpy(host + L::W_HH + (size_t)dst * ntm::H64, w_hh + (size_t)src * H, sizeof(float) * H);
+            host[L::W_IH + dst] = w_ih[src];
+            host[L::B_IH + dst] = b_ih[src];
+            host[L::B_HH + dst] = b_hh[src];
+        }
+    }
+    memcpy(host + L::W_OUT, w_out, sizeof(float) * H);
     host[L::B_OUT] = b_out ? b_out[0] : 0.0f;
     ntm::pack_tc_images(host);
     ntm::TcsConsts tcs;

@@ -11,8 +11,11 @@
 // shared-memory accesses the two warps of a sub-partition push through it, not by a pipe (profiles/r02d_mma_lone_vs_paired.txt:
 // one more LDS per step costs 8 %, ten more instructions 19 %), so the loop is unrolled four steps deep and everything that
 // can be amortised over the four is:
-//   * x is staged per stream with time contiguous ([stream][CH]) and read as ONE LDS.128 per four steps (was one LDS per step
-//     plus its address arithmetic); staging itself moves 16 bytes per cp.async where the rows allow it;
+//   * x is staged per stream with time contiguous ([stream][CH + 8]) and read as ONE LDS.128 per four steps (was one LDS per step
+//     plus its address arithmetic); staging itself moves 16 bytes per cp.async where the rows allow it.  The 8 floats of row
+//     padding matter: with rows exactly CH = 128 floats apart the four streams' float4s sit in the same banks and the LDS.128 is
+//     served in four passes -- 204.4 ns/step at 1024 streams against 194.5 with any padding that spreads them (4 .. 24 floats
+//     measured alike), 164.4 -> 161.7 at batch 1, cfg 3 173.2 -> 171.3 (profiles/r02f_lean_chunk_pad_sweep.txt);
 //   * the head partial sums of four steps leave as ONE STS.128 per warp lane (was an STS.64 + three address instructions per
 //     step), which also keeps the head accumulators away from their HMMA (the "deferred head" effect without its burst);
 //   * the two state tiles alternate at compile time (no tile address arithmetic, no toggle), the loop counter and its compare
@@ -32,17 +35,27 @@ using namespace mmaf;
 namespace {
 
 constexpr float LOG2E_F4 = 1.4426950408889634f;
+#ifndef NTM_MMA4_CH
+#define NTM_MMA4_CH 128          // steps per staged chunk (A/B knob, tools/ab_build.py)
+#endif
+#ifndef NTM_MMA4_XPAD
+#define NTM_MMA4_XPAD 8          // padding of a staged x row in floats (A/B knob)
+#endif
+#ifndef NTM_MMA4_YPAD
+#define NTM_MMA4_YPAD 4          // padding of a head-partial row in floats, >= 4 (A/B knob)
+#endif
 
 template <int FMT>
 struct Mma4Cfg {
     using F = Frag<FMT, false>;
     static constexpr int SC = 4;                     // streams per CTA (columns 0, 2, 4, 6 of the n8 tile)
-    static constexpr int CH = 128;                   // steps per staged chunk
-    static constexpr int YLD = CH + 4;               // head partials of one (warp, stream): position p holds sample p - 1
+    static constexpr int CH = NTM_MMA4_CH;           // steps per staged chunk
+    static constexpr int XLD = CH + NTM_MMA4_XPAD;   // staged x row of one stream
+    static constexpr int YLD = CH + NTM_MMA4_YPAD;   // head partials of one (warp, stream): position p holds sample p - 1
     static constexpr int TILE_BYTES = 8 * F::ROW_BYTES;
     static constexpr int OFF_HB = 0;                                         // [2][8][ROW_BYTES]
     static constexpr int OFF_XS = (2 * TILE_BYTES + 127) / 128 * 128;        // [2][SC][CH] floats
-    static constexpr int OFF_YP = OFF_XS + 2 * SC * CH * 4;                  // [4 warps][SC][YLD] floats
+    static constexpr int OFF_YP = OFF_XS + 2 * SC * XLD * 4;                 // [4 warps][SC][YLD] floats
     static constexpr int OFF_DS = OFF_YP + 4 * SC * YLD * 4;                 // [2][SC][CH] delay trajectory (DiffDelRNN)
     static constexpr int SMEM_BYTES = OFF_DS + 2 * SC * CH * 4;              // + the pre_d ring [SC][ring_len], sized at launch
 };
@@ -65,7 +78,7 @@ __global__ void __launch_bounds__(128, 2) gru_mma4_kernel(const GruArgs a)
     constexpr int NP = STRICT ? 2 : 1;
     using C = Mma4Cfg<FMT>;
     using F = Frag<FMT, false>;
-    constexpr int SC = C::SC, CH = C::CH, NK = F::NK, YLD = C::YLD;
+    constexpr int SC = C::SC, CH = C::CH, NK = F::NK, YLD = C::YLD, XLD = C::XLD;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* const hb = smem + C::OFF_HB;
     float* const xs = reinterpret_cast<float*>(smem + C::OFF_XS);
@@ -123,18 +136,18 @@ __global__ void __launch_bounds__(128, 2) gru_mma4_kernel(const GruArgs a)
     const bool vec = ((reinterpret_cast<uintptr_t>(a.x) | (uintptr_t)(a.ldx * 4)) & 15) == 0;
     auto load_x = [&](int buf, long long t0) {
         const int n = (int)((a.T - t0) < (long long)CH ? (a.T - t0) : (long long)CH);
-        float* dstb = xs + buf * SC * CH;
+        float* dstb = xs + buf * SC * XLD;
         if (vec && n == CH) {
             for (int idx = tid; idx < SC * CH / 4; idx += 128) {
                 const int s = idx / (CH / 4), q = idx % (CH / 4);
-                if (s < ns) cp_async16(dstb + s * CH + 4 * q, a.x + (b0 + s) * a.ldx + t0 + 4 * q);
-                else *reinterpret_cast<float4*>(dstb + s * CH + 4 * q) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                if (s < ns) cp_async16(dstb + s * XLD + 4 * q, a.x + (b0 + s) * a.ldx + t0 + 4 * q);
+                else *reinterpret_cast<float4*>(dstb + s * XLD + 4 * q) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             }
         } else {
             for (int idx = tid; idx < SC * CH; idx += 128) {
                 const int s = idx / CH, tt = idx % CH;
-                if (s < ns && tt < n) cp_async4(dstb + idx, a.x + (b0 + s) * a.ldx + t0 + tt);
-                else dstb[idx] = 0.0f;
+                if (s < ns && tt < n) cp_async4(dstb + s * XLD + tt, a.x + (b0 + s) * a.ldx + t0 + tt);
+                else dstb[s * XLD + tt] = 0.0f;
             }
         }
         cp_async_commit();
@@ -264,7 +277,7 @@ __global__ void __launch_bounds__(128, 2) gru_mma4_kernel(const GruArgs a)
         const long long t0 = c * CH;
         const int n = (int)((a.T - t0) < (long long)CH ? (a.T - t0) : (long long)CH);
         const int xb = (int)(c & 1);
-        const float* xcur = xs + xb * SC * CH;
+        const float* xcur = xs + xb * SC * XLD;
         cp_async_wait_all();
         __syncthreads();                       // xs[xb] landed; state tile `cur` complete; previous flush done
         if (c + 1 < nchunks) {
@@ -272,7 +285,7 @@ __global__ void __launch_bounds__(128, 2) gru_mma4_kernel(const GruArgs a)
             if (use_ring) load_d(xb ^ 1, t0 + CH);
         }
 
-        const float* xrow = xcur + tig * CH;
+        const float* xrow = xcur + tig * XLD;
         int tt = 0;
         if (cur == 0) {
             for (; tt + 4 <= n; tt += 4) {
@@ -304,7 +317,7 @@ __global__ void __launch_bounds__(128, 2) gru_mma4_kernel(const GruArgs a)
             if (s < ns && t < n) {
                 float v = yp[s * YLD + t + 1] + yp[(SC + s) * YLD + t + 1] + yp[(2 * SC + s) * YLD + t + 1] +
                           yp[(3 * SC + s) * YLD + t + 1] + bo;
-                if (a.skip) v += xcur[s * CH + t];
+                if (a.skip) v += xcur[s * XLD + t];
                 head_out[(b0 + s) * ldo + t0 + t] = v;
                 if (delay && a.warmup) a.y[(b0 + s) * a.ldy + t0 + t] = v;
                 if (use_ring) ring[s * a.ring_len + ((int)(t0 + t) & rmask)] = v;

@@ -28,6 +28,7 @@ import torch
 from . import lib as _lib
 
 WARM_LEN = 2 ** 10      # code/model.py:60, :386
+ENGINE_H = 64           # state width of the kernels (ntm::H64); smaller hidden sizes run zero-padded
 
 
 def _ptr(t):
@@ -100,9 +101,10 @@ class _Engine:
             H = params[1].shape[1]
             if params[0].shape[1] != 1 or head.weight.shape[0] != 1:
                 raise RuntimeError("ntm_b200: only input_size=1, output_size=1 models are supported")
-            if H != 64:
-                raise RuntimeError(f"ntm_b200: only hidden_size=64 is built into the engine (all shipped checkpoints are "
-                                   f"GRU-HS[64]); this module has hidden_size={H}")
+            if not 1 <= H <= ENGINE_H:
+                raise RuntimeError(f"ntm_b200: the engine is built for hidden_size <= {ENGINE_H} (all shipped checkpoints are "
+                                   f"GRU-HS[64]; smaller models run zero-padded to 64 units, exactly); this module has "
+                                   f"hidden_size={H}")
             ops = _lib.ops()
             handle = int(ops.prepare(*[p.detach() if p is not None else None for p in params], device.index))
             self.handle, self._device = handle, device
@@ -179,6 +181,7 @@ class RNN(torch.nn.Module):
         return self._engine.get(self.GRU, self.output, device)
 
     def _hidden_in(self, B, device):
+        """self.hidden checked like torch.nn.GRU checks it, as the engine's (1, B, 64) state (see _to_engine)."""
         h = self.hidden
         if h is None:
             return None
@@ -186,7 +189,20 @@ class RNN(torch.nn.Module):
             raise RuntimeError(f"Expected hidden size (1, {B}, {self.hidden_size}), got {list(h.shape)}")
         if h.device != device or h.dtype != torch.float32 or not h.is_contiguous():
             h = h.to(device, torch.float32).contiguous()
-        return h
+        return self._to_engine(h)
+
+    # The engine's state is always ENGINE_H = 64 units wide.  A model with hidden_size < 64 runs zero-padded: the padded units
+    # have zero weights in and out, so their state stays 0 (r = z = 1/2, n = tanh(0) = 0) and no real unit ever sees them --
+    # the result is the hidden_size-wide GRU's, term for term.  `self.hidden` keeps the reference's (1, B, hidden_size) shape.
+    def _to_engine(self, h):
+        if h is None or h.shape[-1] == ENGINE_H:
+            return h
+        return torch.nn.functional.pad(h, (0, ENGINE_H - h.shape[-1]))
+
+    def _from_engine(self, h):
+        if h is None or self.hidden_size == ENGINE_H:
+            return h
+        return h[..., :self.hidden_size].contiguous()
 
     def warm_start(self):
         """1024 samples of silence from the current state, batch 1 (code/model.py:58-65)."""
@@ -201,8 +217,8 @@ class RNN(torch.nn.Module):
         handle = self._handle(dev)
         B = x.shape[0]
         h_in = self.hidden
-        if h_in is not None and not (h_in.shape[1] == B and h_in.device == dev and h_in.dtype is torch.float32
-                                     and h_in.is_contiguous()):
+        if h_in is not None and not (h_in.shape[1] == B and h_in.shape[2] == ENGINE_H and h_in.device == dev
+                                     and h_in.dtype is torch.float32 and h_in.is_contiguous()):
             h_in = self._hidden_in(B, dev)
         ops = _lib.ops()
         if self.static_io:
@@ -210,12 +226,12 @@ class RNN(torch.nn.Module):
             buf = self._io.get(key)
             if buf is None:
                 buf = self._io[key] = (torch.empty((B, 1, x.shape[2]), dtype=torch.float32, device=dev),
-                                       torch.empty((1, B, self.hidden_size), dtype=torch.float32, device=dev))
+                                       torch.empty((1, B, ENGINE_H), dtype=torch.float32, device=dev))
             y, h_out = buf
             ops.gru_forward_out(handle, _lib.MODES[self.mode], x, h_in, y, h_out, bool(self.skip))
         else:
             y, h_out = ops.gru_forward(handle, _lib.MODES[self.mode], x, h_in, bool(self.skip))
-        self.hidden = h_out
+        self.hidden = h_out if self.hidden_size == ENGINE_H else self._from_engine(h_out)
         return y
 
     def block_stream(self, n_streams=1, block_len=64):
@@ -256,12 +272,12 @@ class RNN(torch.nn.Module):
         B, T = x.shape[0], x.shape[2]
         self.initialize_hidden()
         self.warm_start()
-        h = self.hidden.reshape(1, self.hidden_size).expand(B, self.hidden_size).contiguous().cpu()
+        h = self._to_engine(self.hidden).reshape(1, ENGINE_H).expand(B, ENGINE_H).contiguous().cpu()
         y = _host_out(out, (B, 1, T), "out", torch.float16 if half else torch.float32)
         fn = _lib.load().ntm_gru_predict_host_f16 if half else _lib.load().ntm_gru_predict_host
         rc = fn(handle, _lib.MODES[self.mode], _ptr(x), _ptr(y), _ptr(h), B, T, int(bool(self.skip)), int(chunk))
         _lib.check(rc)
-        self.hidden = h.reshape(1, B, self.hidden_size).to(dev)
+        self.hidden = self._from_engine(h.reshape(1, B, ENGINE_H)).to(dev)
         return y
 
 
@@ -283,7 +299,7 @@ class BlockStream:
         self._mode = _lib.MODES[model.mode]
         self._skip = int(bool(model.skip))
         h = model._hidden_in(self.B, dev)
-        self.h = torch.zeros((1, self.B, model.hidden_size), dtype=torch.float32, device=dev) if h is None else h.clone()
+        self.h = torch.zeros((1, self.B, ENGINE_H), dtype=torch.float32, device=dev) if h is None else h.clone()
         self.y = torch.empty((self.B, 1, self.T), dtype=torch.float32, device=dev)
         self._fn = _lib.load().ntm_gru_forward
         self._hp = ctypes.c_void_p(self.h.data_ptr())
@@ -309,7 +325,7 @@ class BlockStream:
 
     def close(self):
         """Hand the carried state back to the model (`model.hidden`)."""
-        self.model.hidden = self.h
+        self.model.hidden = self.model._from_engine(self.h)
         return self.model.hidden
 
 
@@ -330,7 +346,7 @@ class RealtimeStream:
             raise RuntimeError("ntm_b200 has no CPU path; move the model to a CUDA device")
         self.model, self.B, self.T, self.device = model, int(n_streams), int(block_len), dev
         h = model._hidden_in(self.B, dev)
-        h_host = None if h is None else h.reshape(self.B, model.hidden_size).to("cpu", torch.float32).contiguous()
+        h_host = None if h is None else h.reshape(self.B, ENGINE_H).to("cpu", torch.float32).contiguous()
         torch.cuda.current_stream(dev).synchronize()         # the state above is final before the server reads its copy
         self._rt = ctypes.c_void_p()
         rc = _lib.load().ntm_rt_open(model._handle(dev), _lib.MODES[model.mode], _ptr(h_host), self.B, self.T,
@@ -365,10 +381,10 @@ class RealtimeStream:
         """Stop the resident kernel and hand the carried state back to the model (`model.hidden`)."""
         if self._rt is None:
             return self.model.hidden
-        h = torch.empty((self.B, self.model.hidden_size), dtype=torch.float32)
+        h = torch.empty((self.B, ENGINE_H), dtype=torch.float32)
         rt, self._rt = self._rt, None
         _lib.check(_lib.load().ntm_rt_close(rt, _ptr(h)))
-        self.model.hidden = h.reshape(1, self.B, self.model.hidden_size).to(self.device)
+        self.model.hidden = self.model._from_engine(h.reshape(1, self.B, ENGINE_H)).to(self.device)
         return self.model.hidden
 
     def __del__(self):
@@ -471,8 +487,9 @@ class DiffDelRNN(RNN):
         h_in = self._hidden_in(B, dev)
         hist = self.diffdel._history(B, dev)
         self.diffdel._check(d)
-        y, pre_d, self.hidden, self.diffdel.buffer = _lib.ops().diffdel_forward(
+        y, pre_d, h_out, self.diffdel.buffer = _lib.ops().diffdel_forward(
             handle, _lib.MODES[self.mode], x, d, h_in, hist, bool(warmup), bool(self.skip))
+        self.hidden = self._from_engine(h_out)
         return y, pre_d
 
     def predict(self, input, d_traj):
@@ -501,13 +518,13 @@ class DiffDelRNN(RNN):
         self.initialize_hidden(1, self.max_delay)
         self.warm_start()
         D = int(self.diffdel.max_delay)
-        h = self.hidden.reshape(1, self.hidden_size).expand(B, self.hidden_size).contiguous().cpu()
+        h = self._to_engine(self.hidden).reshape(1, ENGINE_H).expand(B, ENGINE_H).contiguous().cpu()
         hist = self.diffdel.buffer.reshape(1, D).expand(B, D).contiguous().cpu()
         y = _host_out(out, (B, 1, T), "out")
         pre = _host_out(out_pre_d, (B, 1, T), "out_pre_d")
         rc = _lib.load().ntm_diffdel_predict_host(handle, _lib.MODES[self.mode], _ptr(x), _ptr(d), _ptr(y), _ptr(pre),
                                                   _ptr(h), _ptr(hist), B, T, D, int(bool(self.skip)), int(chunk))
         _lib.check(rc)
-        self.hidden = h.reshape(1, B, self.hidden_size).to(dev)
+        self.hidden = self._from_engine(h.reshape(1, B, ENGINE_H)).to(dev)
         self.diffdel.buffer = hist.reshape(B, 1, D).to(dev)
         return y, pre
