@@ -384,10 +384,10 @@ def main():
         "roofline": {
             "bound": "tensor", "achieved": achieved_tflops, "peak": tensor_peak, "unit": "TFLOP/s",
             "frac": achieved_tflops / tensor_peak,
-            # dram__bytes_read+write of this kernel from one `ncu --set full` capture (profiles/r01_mma_b1024_ncu.txt:
-            # 395.3 MB read + 355.4 MB written for 1024 x 96 000 samples = 7.64 B per sample against 8 algorithmic -- the
-            # last ~10 % of the y writes were still in the 126 MB L2 when the kernel ended), scaled to this launch
-            "traffic": round(750.7e6 / (1024 * 96000) * B * T), "algorithmic_bytes": BYTES_PER_SAMPLE * B * T,
+            # dram__bytes_read+write of this kernel from one `ncu --set full` capture (profiles/r02f_mma_b1024_ncu.txt,
+            # gru_mma4_kernel: 395.7 MB read + 352.8 MB written for 1024 x 96 000 samples = 7.61 B per sample against 8
+            # algorithmic -- the last ~10 % of the y writes were still in the 126 MB L2 when the kernel ended), scaled to this launch
+            "traffic": round(748.5e6 / (1024 * 96000) * B * T), "algorithmic_bytes": BYTES_PER_SAMPLE * B * T,
             "traffic_source": "estimated_from_profile: bytes per sample of the ncu capture at 1024 x 96 000, scaled to this launch",
             "peak_source": peak_src,
             "kernel_ms": kern_ms, "kernel": kernel_name,
