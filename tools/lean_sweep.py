@@ -48,3 +48,25 @@ with torch.inference_mode():
     ms = best_of(lambda: md.predict(x, d))
     row.append(f"cfg3 f16 {ms*1e6/(T+1024):6.1f}")
 print(os.path.basename(lib.LIB_PATH).replace("libntm_b200", "").replace(".so", "") or "product", "|", " | ".join(row), flush=True)
+
+# accuracy of the same build on golden signals (automatic dispatch = the lean kernel at batch 1): ESR against the reference's fp32 output
+from conftest import load_golden
+from oracle import c_oracle
+import numpy as np
+acc = []
+with torch.inference_mode():
+    for tag in ("cfg1", "cfg2"):
+        g = load_golden(f"golden_{tag}")
+        m = ntm_b200.RNN(1, 64, 1, False).to(dev)
+        m.load_state_dict(load_ckpt(tag))
+        for mode in ("f16", "f16x3"):
+            m.mode = mode
+            for sig in ("sweepnoise", "noise", "sine"):
+                y = m.predict(torch.from_numpy(g[f"x_{sig}"]).to(dev).reshape(1, 1, -1)).cpu().numpy().reshape(-1)
+                acc.append(f"{tag} {mode} {sig} esr={c_oracle.esr(y, g[f'y_{sig}']):.2e} max={np.max(np.abs(y - g[f'y_{sig}'])):.1e}")
+    g = load_golden("golden_cfg3")
+    md.mode = "f16"
+    for sig in ("sweepnoise", "pulse", "sine"):
+        y, pre = md.predict(torch.from_numpy(g[f"x_{sig}"]).to(dev).reshape(1, 1, -1), torch.from_numpy(g[f"d_{sig}"]).to(dev).reshape(1, 1, -1))
+        acc.append(f"cfg3 f16 {sig} esr={c_oracle.esr(y.cpu().numpy().reshape(-1), g[f'y_{sig}']):.2e}")
+print("   " + " | ".join(acc), flush=True)

@@ -20,7 +20,8 @@ from conftest import SIGNALS, load_ckpt, load_golden
 DEV = "cuda:0"
 L = lib.load()
 # (mode, kernel selector, label)
-CASES = [("fp32", (0, 0)), ("f16x3", (4, 3)), ("f16x3", (8, 3)), ("f16x3", (1, 4)), ("f16", (4, 3)), ("f16", (8, 3)), ("f16", (1, 4)),
+CASES = [("fp32", (0, 0)), ("f16x3", (4, 3)), ("f16x3", (4, 6)), ("f16x3", (8, 3)), ("f16x3", (1, 4)), ("f16", (4, 3)), ("f16", (4, 6)),
+         ("f16", (8, 3)), ("f16", (1, 4)),
          ("tf32", (8, 3)), ("tf32", (1, 4)), ("bf16", (1, 4))]
 rows = []
 
