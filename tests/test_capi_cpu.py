@@ -53,7 +53,8 @@ def test_argument_validation_without_device():
     assert L.ntm_gru_prepare(None, None, None, None, None, None, 64, 0, ctypes.byref(h)) == -1
     buf = (ctypes.c_float * (192 * 64))()
     p = ctypes.cast(buf, ctypes.c_void_p)
-    assert L.ntm_gru_prepare(p, p, p, p, p, None, 8, 0, ctypes.byref(h)) == -2      # only H = 64 is built
+    assert L.ntm_gru_prepare(p, p, p, p, p, None, 65, 0, ctypes.byref(h)) == -2     # NTM_EUNSUPPORTED: 1 <= H <= 64 is built
+    assert L.ntm_gru_prepare(p, p, p, p, p, None, 0, 0, ctypes.byref(h)) == -2
     if not torch.cuda.is_available():
         assert L.ntm_gru_prepare(p, p, p, p, p, None, 64, 0, ctypes.byref(h)) == -6  # no device, no fallback
     assert L.ntm_gru_forward(None, 0, None, 0, None, 0, None, None, 1, 1, 0, None) == -1   # bad handle
