@@ -323,7 +323,7 @@ cudaError_t launch_gru_fp32(const GruArgs& a, int sm_count, int tune_s, int tune
         while (s < 8 && s < per_cta) s <<= 1;
     }
     if (s != 1 && s != 2 && s != 4) s = 8;
-    // measured on B200 (tools/sweep_fp32.py): the 2-way k-split wins while a CTA owns <= 2 streams
+    // measured on B200 (tools/experiments/sweep_fp32.py): the 2-way k-split wins while a CTA owns <= 2 streams
     int ks = tune_ks > 0 ? tune_ks : (s <= 2 ? 2 : 4);
     if (ks != 2) ks = 4;
     if (ks == 2 && s > 2) ks = 4;

@@ -3,14 +3,14 @@
 import os
 import sys
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import torch
 import ntm_b200
 from ntm_b200 import lib, signals
 
 dev = torch.device("cuda:0")
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 z = np.load(os.path.join(ROOT, "tests/golden/ckpt_cfg2.npz"))
 sd = {k: torch.from_numpy(z[k]) for k in z.files if k not in ("model_type", "weights_dir")}
 m = ntm_b200.RNN(1, 64, 1, False).to(dev)

@@ -3,14 +3,14 @@
 import os
 import sys
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import torch
 import ntm_b200
 from ntm_b200 import lib, signals
 
 dev = torch.device("cuda:0")
-z = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests/golden/ckpt_cfg2.npz"))
+z = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "tests/golden/ckpt_cfg2.npz"))
 sd = {k: torch.from_numpy(z[k]) for k in z.files if k not in ("model_type", "weights_dir")}
 m = ntm_b200.RNN(1, 64, 1, False).to(dev)
 m.load_state_dict(sd)
