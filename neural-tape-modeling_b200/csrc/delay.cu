@@ -9,17 +9,31 @@ namespace ntm {
 namespace {
 
 // VEC: rows of d and y are 16-byte aligned (base and leading dimension): a thread owns DELAY_SPT consecutive samples,
-// loads their delays with 16-byte loads, issues all of its 2 x DELAY_SPT tap gathers as independent instructions, and
-// stores 16 bytes at a time.  One sample per thread and iteration left the pass latency-bound (d -> index -> x -> y is a
-// dependent chain with 4 bytes in flight per thread: 2.44 TB/s); this form reaches 3.73 TB/s.  (Tried: the same with lane-
-// strided samples so that every access of a warp is one 128-byte segment -- 2.57 TB/s: scalar loads put fewer bytes in
-// flight per thread, and bytes in flight are what bounds this two-phase gather; and a persistent block that stages the
-// delays and the reachable x window of a 2048-sample tile in shared memory with double-buffered 16-byte cp.async -- the
-// same 4.66 TB/s at D = 365 and 3.9 TB/s at D = 2000, where consecutive windows overlap by half: dropped.)
+// loads their delays with 16-byte loads, issues its tap gathers as independent instructions, and stores 16 bytes at a time.
+// History of this kernel (1024 x 1 440 000 samples, D = 365; the copy peak of this GPU is 6.54 TB/s, a plain two-reads-one-write
+// elementwise pass -- torch.add -- reaches 6.97; profiles/r02f_delay_line.txt):
+//   one sample per thread                         2.44 TB/s   d -> index -> x -> y is a dependent chain with 4 bytes in flight per thread
+//   8 samples per thread, 16 independent gathers  4.63-4.72   (lane-strided samples: 2.57; shared-memory staging of d and the reachable
+//                                                             x window with double-buffered cp.async: 4.66, 3.9 at D = 2000 -- dropped)
+//   + second tap reused from the neighbour sample 5.20        9 gathers per thread instead of 16: the gathers cost L1 passes
+//   + 32 groups per thread, next delays prefetched 6.38       few long-lived CTAs instead of one CTA per 2048 samples
 constexpr int DELAY_SPT = 8;
+#ifndef NTM_DELAY_REUSE
+#define NTM_DELAY_REUSE 1
+#endif
+#ifndef NTM_DELAY_ITER
+#define NTM_DELAY_ITER 32
+#endif
+// Few, long-lived CTAs: a thread walks over up to DELAY_ITER groups of its row (a grid stride apart) and loads the delays of its next
+// group before it gathers the taps of the current one -- one exposed HBM round trip per group instead of two dependent ones, and
+// no CTA launch per 2048 samples.  Measured at 1024 x 1 440 000, D = 365 (profiles/r02f_delay_line.txt): 4.63 TB/s with one group
+// per thread, 5.20 with the tap reuse below, 5.85 / 6.07 / 6.18 / 6.36 at 4 / 8 / 16 / 32 groups per thread.  Small problems keep one
+// group per thread (the launcher never drops below DELAY_MIN_CTAS_PER_SM CTAs per SM).
+constexpr int DELAY_ITER = NTM_DELAY_ITER;
+constexpr int DELAY_MIN_CTAS_PER_SM = 12;
 
 template <bool VEC>
-__global__ void __launch_bounds__(256, 4) delay_kernel(const float* __restrict__ x, long long ldx,
+__global__ void __launch_bounds__(256, 3) delay_kernel(const float* __restrict__ x, long long ldx,
                                                     const float* __restrict__ d, long long ldd,
                                                     float* __restrict__ y, long long ldy,
                                                     const float* __restrict__ hist_in, long long B, long long T,
@@ -33,15 +47,22 @@ __global__ void __launch_bounds__(256, 4) delay_kernel(const float* __restrict__
     auto past = [&](long long i) { return i >= 0 ? __ldg(xr + i) : __ldg(hr + D + i); };
     {
         const long long groups = T / DELAY_SPT;
-        for (long long gq = (long long)blockIdx.x * blockDim.x + threadIdx.x; gq < groups;
-             gq += (long long)gridDim.x * blockDim.x) {
+        const long long stride = (long long)gridDim.x * blockDim.x;
+        long long gq = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+        static_assert(DELAY_SPT == 8, "two float4 of delays per group");
+        float4 dn0 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), dn1 = dn0;
+        if (VEC && gq < groups) {
+            dn0 = __ldg(reinterpret_cast<const float4*>((warmup ? xr : dr) + gq * DELAY_SPT));
+            dn1 = __ldg(reinterpret_cast<const float4*>((warmup ? xr : dr) + gq * DELAY_SPT) + 1);
+        }
+        for (; gq < groups; gq += stride) {
             const long long t = gq * DELAY_SPT;
             float dv[DELAY_SPT], v[DELAY_SPT];
             if (VEC) {
-#pragma unroll
-                for (int q = 0; q < DELAY_SPT / 4; ++q) {
-                    const float4 a = __ldg(reinterpret_cast<const float4*>((warmup ? xr : dr) + t) + q);
-                    dv[4 * q] = a.x; dv[4 * q + 1] = a.y; dv[4 * q + 2] = a.z; dv[4 * q + 3] = a.w;
+                dv[0] = dn0.x; dv[1] = dn0.y; dv[2] = dn0.z; dv[3] = dn0.w; dv[4] = dn1.x; dv[5] = dn1.y; dv[6] = dn1.z; dv[7] = dn1.w;
+                if (gq + stride < groups) {
+                    dn0 = __ldg(reinterpret_cast<const float4*>((warmup ? xr : dr) + (gq + stride) * DELAY_SPT));
+                    dn1 = __ldg(reinterpret_cast<const float4*>((warmup ? xr : dr) + (gq + stride) * DELAY_SPT) + 1);
                 }
             } else {                                              // rows not 16-byte aligned: same grouping, 4-byte accesses
 #pragma unroll
@@ -67,10 +88,14 @@ __global__ void __launch_bounds__(256, 4) delay_kernel(const float* __restrict__
                 const float* xt = xr + t;
                 if (t > (long long)D) {                           // no tap of this group can reach the carried history
 #pragma unroll
-                    for (int j = 0; j < DELAY_SPT; ++j) {
-                        p[j][0] = __ldg(xt + off[j][0]);
-                        p[j][1] = __ldg(xt + off[j][1]);
-                    }
+                    for (int j = 0; j < DELAY_SPT; ++j) p[j][0] = __ldg(xt + off[j][0]);
+                    // the second tap of sample j is the first tap of sample j - 1 whenever both delays have the same integer
+                    // part (x[t + j - fl - 1] either way): the load is predicated off then -- 9 gathers per thread instead of
+                    // 16 on a smooth trajectory, same values
+                    p[0][1] = __ldg(xt + off[0][1]);
+#pragma unroll
+                    for (int j = 1; j < DELAY_SPT; ++j)
+                        p[j][1] = (NTM_DELAY_REUSE && off[j][1] == off[j - 1][0]) ? p[j - 1][0] : __ldg(xt + off[j][1]);
                 } else {
                     const float* ht = hr + D + t;
 #pragma unroll
@@ -127,6 +152,14 @@ __global__ void __launch_bounds__(256) delay_check_kernel(const float* __restric
     if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(flag, 1);
 }
 
+int sm_count()          // of the current device
+{
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+        return 148;
+    return n;
+}
+
 unsigned grid_x(long long n)
 {
     long long g = (n + 255) / 256;
@@ -149,7 +182,15 @@ cudaError_t launch_delay(const float* x, long long ldx, const float* d, long lon
             const float* src = warmup ? x : d;
             const long long lds = warmup ? ldx : ldd;
             const bool vec = (((unsigned long long)src | (unsigned long long)y) & 15ull) == 0 && (lds & 3) == 0 && (ldy & 3) == 0;
-            const dim3 grid(grid_x((T + DELAY_SPT - 1) / DELAY_SPT), (unsigned)nb);
+            // x-blocks per row: DELAY_ITER groups per thread, but at least DELAY_MIN_CTAS_PER_SM CTAs per SM over all rows and at
+            // most one thread per group
+            const long long per_row = (T / DELAY_SPT + 255) / 256;
+            long long want = (per_row + DELAY_ITER - 1) / DELAY_ITER;
+            const long long floor_ctas = ((long long)sm_count() * DELAY_MIN_CTAS_PER_SM + nb - 1) / nb;
+            if (want < floor_ctas) want = floor_ctas;
+            if (want > per_row) want = per_row;
+            if (want < 1) want = 1;
+            const dim3 grid(grid_x(want * 256), (unsigned)nb);
             if (vec)
                 delay_kernel<true><<<grid, 256, 0, st>>>(x + b0 * ldx, ldx, d + b0 * ldd, ldd, y + b0 * ldy, ldy,
                                                          hist_in + b0 * D, nb, T, (int)D, warmup);
