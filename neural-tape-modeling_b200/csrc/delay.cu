@@ -46,23 +46,27 @@ __global__ void __launch_bounds__(256, 3) delay_kernel(const float* __restrict__
     float* yr = y + b * ldy;
     auto past = [&](long long i) { return i >= 0 ? __ldg(xr + i) : __ldg(hr + D + i); };
     {
-        const long long groups = T / DELAY_SPT;
-        const long long stride = (long long)gridDim.x * blockDim.x;
-        long long gq = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+        // VEC: this row's d (x in warm-up mode) and y share their position inside a 16-byte line (the launcher checked it); the
+        // first `head` samples up to the line boundary and the last (T - head) % DELAY_SPT go through the scalar tail below
+        const int head = VEC ? (int)((4 - ((reinterpret_cast<uintptr_t>(warmup ? xr : dr) >> 2) & 3)) & 3) : 0;
+        const int groups = T > head ? (int)((T - head) / DELAY_SPT) : 0;       // (the launcher keeps T below 2^34)
+        const float4* __restrict__ src4 = reinterpret_cast<const float4*>((warmup ? xr : dr) + head);   // (VEC only)
+        const int stride = (int)(gridDim.x * blockDim.x);
+        int gq = (int)(blockIdx.x * blockDim.x + threadIdx.x);
         static_assert(DELAY_SPT == 8, "two float4 of delays per group");
         float4 dn0 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), dn1 = dn0;
         if (VEC && gq < groups) {
-            dn0 = __ldg(reinterpret_cast<const float4*>((warmup ? xr : dr) + gq * DELAY_SPT));
-            dn1 = __ldg(reinterpret_cast<const float4*>((warmup ? xr : dr) + gq * DELAY_SPT) + 1);
+            dn0 = __ldg(src4 + 2ll * gq);
+            dn1 = __ldg(src4 + 2ll * gq + 1);
         }
         for (; gq < groups; gq += stride) {
-            const long long t = gq * DELAY_SPT;
+            const long long t = head + (long long)gq * DELAY_SPT;
             float dv[DELAY_SPT], v[DELAY_SPT];
             if (VEC) {
                 dv[0] = dn0.x; dv[1] = dn0.y; dv[2] = dn0.z; dv[3] = dn0.w; dv[4] = dn1.x; dv[5] = dn1.y; dv[6] = dn1.z; dv[7] = dn1.w;
-                if (gq + stride < groups) {
-                    dn0 = __ldg(reinterpret_cast<const float4*>((warmup ? xr : dr) + (gq + stride) * DELAY_SPT));
-                    dn1 = __ldg(reinterpret_cast<const float4*>((warmup ? xr : dr) + (gq + stride) * DELAY_SPT) + 1);
+                if (gq < groups - stride) {
+                    dn0 = __ldg(src4 + 2ll * (gq + stride));
+                    dn1 = __ldg(src4 + 2ll * (gq + stride) + 1);
                 }
             } else {                                              // rows not 16-byte aligned: same grouping, 4-byte accesses
 #pragma unroll
@@ -120,9 +124,9 @@ __global__ void __launch_bounds__(256, 3) delay_kernel(const float* __restrict__
                 for (int j = 0; j < DELAY_SPT; ++j) yr[t + j] = v[j];
             }
         }
-        // the ragged tail (T % DELAY_SPT samples) by the first block
+        // the samples in front of the first group and the ragged tail, by the first block
         if (blockIdx.x == 0) {
-            const long long t = groups * DELAY_SPT + threadIdx.x;
+            const long long t = (int)threadIdx.x < head ? (long long)threadIdx.x : (long long)groups * DELAY_SPT + threadIdx.x;
             if (t < T) yr[t] = warmup ? xr[t] : delay_read(dr[t], t, D, past);
         }
     }
@@ -175,13 +179,17 @@ cudaError_t launch_delay(const float* x, long long ldx, const float* d, long lon
                          cudaStream_t st)
 {
     if (B <= 0) return cudaSuccess;
+    if (T >= (1ll << 33)) return cudaErrorInvalidValue;      // 32-bit group indices inside the kernel (2^33 samples = 2 days of audio per row)
     for (long long b0 = 0; b0 < B; b0 += 65535) {       // gridDim.y limit
         const long long nb = (B - b0) < 65535 ? (B - b0) : 65535;
         if (T > 0) {
             // warm-up copies x -> y: then x takes d's place in the alignment test
             const float* src = warmup ? x : d;
             const long long lds = warmup ? ldx : ldd;
-            const bool vec = (((unsigned long long)src | (unsigned long long)y) & 15ull) == 0 && (lds & 3) == 0 && (ldy & 3) == 0;
+            // 16-byte accesses need every row's src and y at the same position inside a 16-byte line (any position: the
+            // kernel peels up to three samples in front)
+            const bool vec = ((((unsigned long long)(src + b0 * lds)) ^ ((unsigned long long)(y + b0 * ldy))) & 15ull) == 0 &&
+                             (nb == 1 || ((lds - ldy) & 3) == 0);
             // x-blocks per row: DELAY_ITER groups per thread, but at least DELAY_MIN_CTAS_PER_SM CTAs per SM over all rows and at
             // most one thread per group
             const long long per_row = (T / DELAY_SPT + 255) / 256;

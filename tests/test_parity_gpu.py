@@ -259,6 +259,40 @@ def test_delay_line_assert_and_chunking():
         assert np.array_equal(y_all.cpu().numpy()[:, 0], yo)
 
 
+@pytest.mark.parametrize("T,off", [(70001, 0), (70001, 1), (69999, 2), (70003, 3), (131072 + 5, 0), (11, 1)])
+def test_delay_line_row_positions_and_long_rows(T, off):
+    """Rows at every position inside a 16-byte line (odd leading dimensions, views that start mid-line), rows long enough for a
+    thread to walk over several groups with prefetched delays, x and y with different alignment -- bit-exact against the oracle."""
+    B, D = 5, 100
+    rng = np.random.default_rng(T + off)
+    xh = rng.standard_normal((B, T + 8)).astype(np.float32)
+    dh = (rng.random((B, T + 8)) * D).astype(np.float32)
+    dh[0, :] = 37.25 + 30.0 * np.sin(np.arange(T + 8) * 1e-3)              # a smooth trajectory: the tap-reuse path
+    dh[1, ::50] = 0.0
+    dh[1, 1::50] = float(D)                                                  # jumps between the extremes: no reuse
+    hist = rng.standard_normal((B, D)).astype(np.float32)
+    xd, dd = dev(xh), dev(dh)
+    yo, ho = c_oracle.delay_forward(xh[:, off:off + T], dh[:, off:off + T], hist)
+    dl = TimeVaryingDelayLine(max_delay=D)
+    with torch.inference_mode():
+        dv = dd[:, off:off + T].unsqueeze(1)                                 # (B, 1, T) view, rows T + 8 apart, starting mid-line
+        for xoff in (off, (off + 1) % 4):                                    # x at the same / another line position than d
+            xfull = torch.zeros((B, T + 8), device=DEV)
+            xfull[:, xoff:xoff + T] = xd[:, off:off + T]
+            xv = xfull[:, xoff:xoff + T].unsqueeze(1)
+            dl.buffer = dev(hist).reshape(B, 1, D).clone()
+            y = dl(xv, dv)
+            assert np.array_equal(y.cpu().numpy()[:, 0], yo), (T, off, xoff)
+            assert np.array_equal(dl.buffer.cpu().numpy()[:, 0], ho)
+            dl.buffer = dev(hist).reshape(B, 1, D).clone()
+            yw = dl(xv, dv, warmup=True)
+            assert np.array_equal(yw.cpu().numpy()[:, 0], xh[:, off:off + T])
+        # odd leading dimension: contiguous (B, 1, T) tensors whose rows sit at changing line positions
+        dl.buffer = dev(hist).reshape(B, 1, D).clone()
+        y = dl(xd[:, off:off + T].contiguous().unsqueeze(1), dd[:, off:off + T].contiguous().unsqueeze(1))
+        assert np.array_equal(y.cpu().numpy()[:, 0], yo), (T, off, "contiguous")
+
+
 # ------------------------------------------------------------------------------------ DiffDelRNN
 @pytest.mark.parametrize("mode,kernel", STRICT_CLASS)
 def test_diffdel_predict_vs_golden(mode, kernel):
