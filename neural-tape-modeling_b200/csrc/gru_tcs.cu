@@ -49,10 +49,7 @@ constexpr int TS_TILE_COLS = 256;          // TMEM columns reserved per tile: 19
 constexpr int TS_A_OFF = 192;              // first operand column inside a tile's TMEM block
 constexpr uint32_t TS_SBO = 128, TS_LBO = (TS_N / 8) * 128;       // K-major, no swizzle
 constexpr int TS_UG = 8;                   // hidden units per TMEM load group
-#ifndef NTM_TCS_UW
-#define NTM_TCS_UW 2
-#endif
-constexpr int TS_UW = NTM_TCS_UW;          // threads per stream (2: 32 hidden units per thread; 4: 16, one tile per CTA only)
+constexpr int TS_UW = 2;                   // threads per stream
 constexpr float TS_LO_SCALE = 256.0f;      // strict form: h_lo' = (h - h_hi) * 2^8
 #ifndef NTM_TCS_STRICT_OWN_RCP
 // strict form: 1 = every gate its own reciprocal, 0 = r/z of a unit and n of two units share one.  Measured (profiles/
@@ -74,8 +71,8 @@ struct TsFmt {
     static constexpr int NMMA = CHUNKS / 2;                    // one MMA consumes 32 bytes of K
     static constexpr uint32_t B_BYTES = CHUNKS * TS_LBO;
     static constexpr uint32_t OFF_BAR = B_BYTES;               // 6 mbarriers + the TMEM base slot + the job slot
-    static constexpr uint32_t OFF_YP = OFF_BAR + 64;           // [2 tiles][2][TS_UW - 1][128] floats
-    static constexpr uint32_t SMEM_BYTES = OFF_YP + 2 * 2 * (TS_UW - 1) * 128 * 4;
+    static constexpr uint32_t OFF_YP = OFF_BAR + 64;           // [2 tiles][2][128] floats
+    static constexpr uint32_t SMEM_BYTES = OFF_YP + 2 * 2 * 128 * 4;
 };
 
 #ifdef NTM_TCS_TRACE
@@ -329,14 +326,7 @@ __device__ __forceinline__ void tcs_epilogue(const GruArgs& a, const TcsConsts& 
     const long long Trem = a.T - t0;                             // samples of x readable from xp
     const uint32_t t_acc = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(tile * TS_TILE_COLS);
     const uint32_t t_op = t_acc + TS_A_OFF;
-    // head partials of the stream's other threads: [tile][step parity][UH - 1][stream]
-    float* const yslot = ypart + tile * 2 * (TS_UW - 1) * TS_M + s;
-    auto ypeers = [&](long long step) {
-        float v = 0.0f;
-#pragma unroll
-        for (int k = 0; k < TS_UW - 1; ++k) v += yslot[((int)(step & 1) * (TS_UW - 1) + k) * TS_M];
-        return v;
-    };
+    float* const yslot = ypart + tile * 2 * TS_M + s;
 
     // ---- initial state: fp32 in registers, rounded copy (+ the first input sample) into the A operand ----
     float h[NU];
@@ -374,7 +364,7 @@ __device__ __forceinline__ void tcs_epilogue(const GruArgs& a, const TcsConsts& 
         if (UH == 0 && t > 0) {
             // the partner's head partial of the previous step (published before its h_ready arrive, which
             // happens-before the commit this thread just observed)
-            float v = yprev + ypeers(gt - 1);
+            float v = yprev + yslot[((gt - 1) & 1) * TS_M];
             if (a.skip) v += xprev;
             if (valid) yp[t - 1] = v;
         }
@@ -428,7 +418,7 @@ __device__ __forceinline__ void tcs_epilogue(const GruArgs& a, const TcsConsts& 
             tmem_st2(t_op + 32, pack_op<FMT>(xh, x1 - xh), pack_op<FMT>(xh, 1.0f));
         }
         const float v = ys[0] + ys[1];
-        if (UH >= 1) yslot[((int)(gt & 1) * (TS_UW - 1) + UH - 1) * TS_M] = v;
+        if (UH == 1) yslot[(gt & 1) * TS_M] = v;
         // release the next MMA batch of this tile (the job's last step has no successor here)
         tmem_st_wait();
         tc_fence_before();
@@ -441,9 +431,9 @@ __device__ __forceinline__ void tcs_epilogue(const GruArgs& a, const TcsConsts& 
         x0 = x1;
         x1 = x2;
     }
-    asm volatile("bar.sync %0, %1;" ::"r"(1 + tile), "r"(128 * TS_UW) : "memory");     // last partials visible
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + tile), "r"(64 * 4) : "memory");     // last partials visible
     if (UH == 0 && valid) {
-        float v = yprev + ypeers(base + nsteps - 1);
+        float v = yprev + yslot[((base + nsteps - 1) & 1) * TS_M];
         if (a.skip) v += xprev;
         yp[nsteps - 1] = v;
     }
@@ -564,14 +554,10 @@ __global__ void __launch_bounds__(32 * (4 * TS_UW + 1) * TILES, 1) gru_tcs_kerne
             // ================================ epilogue warps ======================================================
             const int tile = warp / (4 * TS_UW);
             const int wq = warp & 3;                 // TMEM lane quarter (== warp id % 4)
-            switch ((warp >> 2) % TS_UW) {           // which slice of the stream's hidden units this warp's threads own
-                case 0: tcs_epilogue<FMT, TILES, VAR, 0>(a, kc, tile, wq, lane, tmem, bars, ypart, group, t0, nsteps, base); break;
-                case 1: tcs_epilogue<FMT, TILES, VAR, 1>(a, kc, tile, wq, lane, tmem, bars, ypart, group, t0, nsteps, base); break;
-#if NTM_TCS_UW == 4
-                case 2: tcs_epilogue<FMT, TILES, VAR, 2>(a, kc, tile, wq, lane, tmem, bars, ypart, group, t0, nsteps, base); break;
-                default: tcs_epilogue<FMT, TILES, VAR, 3>(a, kc, tile, wq, lane, tmem, bars, ypart, group, t0, nsteps, base); break;
-#endif
-            }
+            if (((warp >> 2) & 1) == 0)
+                tcs_epilogue<FMT, TILES, VAR, 0>(a, kc, tile, wq, lane, tmem, bars, ypart, group, t0, nsteps, base);
+            else
+                tcs_epilogue<FMT, TILES, VAR, 1>(a, kc, tile, wq, lane, tmem, bars, ypart, group, t0, nsteps, base);
         }
         base += nsteps;
 
@@ -742,8 +728,6 @@ cudaError_t launch_tcs_var(const GruArgs& a, const TcsConsts& kc, int var, int s
 {
     const bool dynamic = var < 0 || (var & 32) == 0;
     if (var >= 0) var &= 31;
-    if constexpr (TILES * (4 * TS_UW + 1) * 32 > 1024) return cudaErrorInvalidConfiguration;     // (four threads per stream: one tile per CTA)
-    else
     switch (var) {      // experiments: (var & 15) = VAR bits, (var & 32) = static schedule
         case 3: return launch_tcs_one<FMT, TILES, 3>(a, kc, sm_count, dynamic, st);
         case 7: if (FMT < 2) return launch_tcs_one<FMT < 2 ? FMT : 0, TILES, 7>(a, kc, sm_count, dynamic, st);      // (elsewhere 7 == 15)
@@ -769,7 +753,6 @@ cudaError_t launch_gru_tcs(const GruArgs& a0, const TcsConsts& kc, int fmt, int 
     }
     // one tile per SM (time-multiplexed by the job queue) beats two resident tiles until ~190 streams per SM (measured)
     if (tiles <= 0) tiles = a.B >= 190ll * sm_count ? 2 : 1;
-    if (TS_UW == 4) tiles = 1;
     cudaError_t e;
     switch (fmt) {
         case FMT_BF16: e = tiles >= 2 ? launch_tcs_var<FMT_BF16, 2>(a, kc, var, sm_count, st) : launch_tcs_var<FMT_BF16, 1>(a, kc, var, sm_count, st); break;
