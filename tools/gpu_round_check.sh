@@ -14,5 +14,6 @@ if [ "$2" == "profile" ]; then
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:gru_mma -s 1 -c 1 -f -o gpurun_out/${TAG}_mma_b1024 python tools/run_once.py 1024 96000 f16 > gpurun_out/${TAG}_ncu_full.log 2>&1
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:gru_mma -s 1 -c 1 -f -o gpurun_out/${TAG}_mma_strict_b1024 python tools/run_once.py 1024 48000 f16x3 >> gpurun_out/${TAG}_ncu_full.log 2>&1
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:gru_tcs -c 1 -f -o gpurun_out/${TAG}_tcs_b37888 python tools/run_once.py 37888 1500 f16 >> gpurun_out/${TAG}_ncu_full.log 2>&1
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:delay_kernel -s 1 -c 1 -f -o gpurun_out/${TAG}_delay_b1024 python tools/delay_once.py 1024 1440000 365 >> gpurun_out/${TAG}_ncu_full.log 2>&1
   tail -3 gpurun_out/${TAG}_ncu_full.log
 fi
