@@ -154,15 +154,23 @@ __device__ __forceinline__ float delay_read(float dt, long long t, int D, LoadPa
 
 __device__ __forceinline__ float ex2_approx(float x)
 {
+#if NTM_DIAG_NOMUFU       // timing diagnostic only (wrong results): one FMA-pipe instruction in place of the MUFU one
+    return fmaf(x, 0.001f, 1.0f);
+#else
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+#endif
 }
 __device__ __forceinline__ float rcp_approx(float x)
 {
+#if NTM_DIAG_NOMUFU
+    return fmaf(x, -0.001f, 1.0f);
+#else
     float y;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+#endif
 }
 
 // ---- packed fp32 arithmetic (sm_100: add / mul / fma .f32x2 = FADD2 / FMUL2 / FFMA2): one issue slot for two lanes' worth of
