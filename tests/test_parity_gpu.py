@@ -293,6 +293,40 @@ def test_delay_line_row_positions_and_long_rows(T, off):
         assert np.array_equal(y.cpu().numpy()[:, 0], yo), (T, off, "contiguous")
 
 
+def test_detach_hidden_on_device_state():
+    """RNN.detach_hidden / DiffDelRNN.detach_hidden (code/model.py:54-56, :377-379: `hidden.clone().detach()`, the delay buffer too) on
+    the engine's CUDA state: a fresh tensor with the same values, and the sequence continues exactly as without it."""
+    x = torch.from_numpy(signals.stream_batch(3, 3000)).to(DEV).reshape(3, 1, 3000)
+    m = RNN(1, 64, 1, False).to(DEV)
+    m.load_state_dict(load_ckpt("cfg2"))
+    md = DiffDelRNN(1, 64, 1, False, max_delay=signals.DELAY_MAX).to(DEV)
+    md.load_state_dict(load_ckpt("cfg3"))
+    d = torch.from_numpy(signals.delay_trajectory(3, 3000)).to(DEV).reshape(3, 1, 3000)
+    with torch.inference_mode():
+        m.initialize_hidden()
+        ya = torch.cat([m(x[:, :, :1000]), m(x[:, :, 1000:])], 2)
+        ha = m.hidden.clone()
+        m.initialize_hidden()
+        y1 = m(x[:, :, :1000])
+        before = m.hidden
+        m.detach_hidden()
+        assert m.hidden is not before and m.hidden.data_ptr() != before.data_ptr() and torch.equal(m.hidden, before)
+        assert m.hidden.is_cuda and not m.hidden.requires_grad
+        yb = torch.cat([y1, m(x[:, :, 1000:])], 2)
+        assert torch.equal(ya, yb) and torch.equal(m.hidden, ha)
+
+        md.initialize_hidden(3, md.max_delay)
+        ya, pa = md(x, d)
+        md.initialize_hidden(3, md.max_delay)
+        y1, p1 = md(x[:, :, :1700], d[:, :, :1700])
+        hb, bb = md.hidden, md.diffdel.buffer
+        md.detach_hidden()
+        assert md.hidden.data_ptr() != hb.data_ptr() and torch.equal(md.hidden, hb)
+        assert md.diffdel.buffer.data_ptr() != bb.data_ptr() and torch.equal(md.diffdel.buffer, bb)
+        y2, p2 = md(x[:, :, 1700:], d[:, :, 1700:])
+        assert torch.equal(torch.cat([y1, y2], 2), ya) and torch.equal(torch.cat([p1, p2], 2), pa)
+
+
 # ------------------------------------------------------------------------------------ DiffDelRNN
 @pytest.mark.parametrize("mode,kernel", STRICT_CLASS)
 def test_diffdel_predict_vs_golden(mode, kernel):
