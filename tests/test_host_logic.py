@@ -77,3 +77,24 @@ def test_signals_are_seeded():
     assert np.abs(a).max() <= 0.75
     d = signals.delay_trajectory(2, 48000)
     assert d.max() <= 292.0 + 1e-3 and d.min() >= 188.0 - 1e-3 and signals.DELAY_MAX == 365
+
+
+def test_hidden_state_padding_helpers():
+    """Hidden sizes below 64 run zero-padded in the 64-unit kernels: `self.hidden` keeps the reference's (1, B, H) shape, the engine sees
+    (1, B, 64) with zeros behind (model.py: _to_engine / _from_engine); the goldens of tests/test_hidden_sizes.py load strictly."""
+    for H in (1, 8, 16, 32, 63, 64):
+        m = RNN(1, H, 1, False)
+        h = torch.arange(3 * H, dtype=torch.float32).reshape(1, 3, H)
+        e = m._to_engine(h)
+        assert tuple(e.shape) == (1, 3, 64) and torch.equal(e[..., :H], h) and float(e[..., H:].abs().sum()) == 0.0
+        back = m._from_engine(e)
+        assert tuple(back.shape) == (1, 3, H) and torch.equal(back, h) and back.is_contiguous()
+        assert m._to_engine(None) is None and m._from_engine(None) is None
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_hs.npz"))
+    for i in range(int(g["n"])):
+        pre = f"w{i}_"
+        sd = {k[len(pre):]: torch.from_numpy(g[k]) for k in g.files if k.startswith(pre)}
+        H = int(g[f"H{i}"])
+        m = RNN(1, H, 1, bool(g[f"skip{i}"])) if str(g[f"kind{i}"]) == "GRU" else DiffDelRNN(1, H, 1, False, max_delay=int(g["max_delay"]))
+        m.load_state_dict(sd, strict=True)
+        assert m.GRU.weight_hh_l0.shape == (3 * H, H)
