@@ -39,6 +39,18 @@ __device__ __forceinline__ uint32_t bf16_pair(float lo, float hi)     // {hi, lo
     return y;
 }
 
+// Ring position of word w (DCPreESR window).  A lane owns ESR_SPL = 8 consecutive words, so the lanes of a quarter warp touch every
+// other 16-byte chunk and, unswizzled, lanes i and i + 4 share their banks (a 2-way conflict on every 16-byte ring access: 17.6 extra
+// shared-memory passes per 256-sample tile, ncu of the round-1 kernel).  Flipping the low chunk bit in every other group of eight chunks
+// makes the eight accesses of a quarter warp cover all 32 banks.
+#ifndef NTM_ESR_SWIZZLE
+#define NTM_ESR_SWIZZLE 1
+#endif
+__device__ __forceinline__ int ring_sw(int w)
+{
+    return NTM_ESR_SWIZZLE ? (w ^ ((w >> 3) & 4)) : w;
+}
+
 __device__ __forceinline__ double warp_sum(double v)
 {
 #pragma unroll
@@ -158,16 +170,16 @@ __global__ void __launch_bounds__(32 * esr_warps(DCPRE)) esr_kernel(const float*
                 uint32_t dl[SPL + 1];
 #pragma unroll
                 for (int q = 0; q < SPL / 4; ++q) {
-                    const uint4 c = *reinterpret_cast<const uint4*>(ring + ((rp + 4 * q) & (ESR_RING - 1)));
+                    const uint4 c = *reinterpret_cast<const uint4*>(ring + ring_sw((rp + 4 * q) & (ESR_RING - 1)));
                     dl[4 * q] = c.x; dl[4 * q + 1] = c.y; dl[4 * q + 2] = c.z; dl[4 * q + 3] = c.w;
                 }
                 dl[SPL] = __shfl_down_sync(0xffffffffu, dl[0], 1);
-                if (lane == 31) dl[SPL] = ring[(rp + SPL) & (ESR_RING - 1)];
+                if (lane == 31) dl[SPL] = ring[ring_sw((rp + SPL) & (ESR_RING - 1))];
                 __syncwarp();
                 const int wp = (int)((nb + SPL * lane) & (ESR_RING - 1));
 #pragma unroll
                 for (int q = 0; q < SPL / 4; ++q)
-                    *reinterpret_cast<uint4*>(ring + wp + 4 * q) =
+                    *reinterpret_cast<uint4*>(ring + ring_sw(wp + 4 * q)) =
                         make_uint4(bf16_pair(xt[4 * q], xe[4 * q]), bf16_pair(xt[4 * q + 1], xe[4 * q + 1]),
                                    bf16_pair(xt[4 * q + 2], xe[4 * q + 2]), bf16_pair(xt[4 * q + 3], xe[4 * q + 3]));
 #pragma unroll
