@@ -611,10 +611,18 @@ def aux_measurements(ntm_b200, signals, dev, mode):
         B = x.shape[0]
         L.ntm_set_tuning(*tuning)
         m.predict(x[:, :, :1200])
-        m.initialize_hidden(); m.warm_start(); m.hidden = m.hidden.expand(1, B, 64).contiguous()
-        e0.record(); m(x); e1.record(); torch.cuda.synchronize(dev)
+        m.initialize_hidden(); m.warm_start()
+        hw = m.hidden.expand(1, B, 64).contiguous()
+        # one untimed full-size call first: the first call of a shape allocates its output inside torch's caching allocator
+        # (a cudaMalloc of up to 0.8 GB in the timed region made single measurements here swing by a factor of 6), then best of two
+        best = float("inf")
+        for rep in range(3):
+            m.hidden = hw.clone()
+            e0.record(); m(x); e1.record(); torch.cuda.synchronize(dev)
+            if rep:
+                best = min(best, e0.elapsed_time(e1))
         L.ntm_set_tuning(0, 0)
-        return B * x.shape[2] / (e0.elapsed_time(e1) * 1e-3)
+        return B * x.shape[2] / (best * 1e-3)
 
     # the same 1024-stream workload (2 s of it) in every arithmetic mode, and the tcgen05 kernel forced
     x2 = signals.stream_batch_device(1024, 96000, dev, dur=60.0).reshape(1024, 1, 96000)
@@ -670,9 +678,12 @@ def aux_measurements(ntm_b200, signals, dev, mode):
         md.mode = mdm
         md.predict(xd[:, :, :4800], dd[:, :, :4800])
         torch.cuda.synchronize(dev)
-        e0.record(); yd, pd = md.predict(xd, dd); e1.record(); torch.cuda.synchronize(dev)
-        cfg3[mdm] = Bd * Td / (e0.elapsed_time(e1) * 1e-3)
-        del yd, pd
+        best = float("inf")
+        for _ in range(2):                        # (the first full-size call allocates its two outputs inside the timed region)
+            e0.record(); yd, pd = md.predict(xd, dd); e1.record(); torch.cuda.synchronize(dev)
+            best = min(best, e0.elapsed_time(e1))
+            del yd, pd
+        cfg3[mdm] = Bd * Td / (best * 1e-3)
     out["cfg3_diffdel_256x30s_samples_per_s"] = cfg3
     del xd, dd
     # evaluation losses on the device: one pass over 1024 streams x 30 s of (output, target);
