@@ -128,8 +128,10 @@ int run_gru(Handle* hd, int mode, const ntm::GruArgs& a, cudaStream_t st)
             // forced with tuning (4, 6); (4, 3) keeps the general kernel
             // (the strict form only while every CTA has an SM of its own: with two CTAs per SM the general kernel's 4-stream
             // form is faster, 361.7 vs 366.8 ns/step at 1024 streams)
+            // (f16 / bf16 up to THREE such CTAs per SM: 5.19 vs 5.03e9 samples/s at 1480 streams, 6.23 vs 6.04 at 1776 against the 8-stream
+            // form; beyond 12 streams per SM the 8-stream form wins: 6.96 vs 5.08 at 2048)
             const bool lean_ok = fmt == 0 || fmt == 1 || fmt == 3;
-            const bool lean_auto = nt == 0 && (fmt != 3 || a.B <= 4ll * hd->sm_count);
+            const bool lean_auto = fmt == 3 ? a.B <= 4ll * hd->sm_count : a.B <= 12ll * hd->sm_count;
             const bool lean = lean_ok && (tg == 6 || (tg == 0 && lean_auto));
             if (lean) CU(ntm::launch_gru_mma4(a, fmt, st));
             else CU(ntm::launch_gru_mma(a, fmt, nt, st));
