@@ -25,7 +25,16 @@ namespace {
 constexpr int ESR_TAPS = 2000;
 constexpr int ESR_WARM = 2048;           // >= ESR_TAPS - 1, multiple of the 128-sample tile
 constexpr int ESR_SPL = 8;               // samples per lane and scan (multiple of 4): the 5 shuffle steps are paid per 32 x SPL samples
-constexpr int ESR_PF = 2;                // tiles of global loads in flight per warp
+#ifndef NTM_ESR_PF
+#define NTM_ESR_PF 4
+#endif
+// 1: a load buffer is consumed IN PLACE and refilled at the end of its tile.  Refilling it at the top (round 1) put the loads one tile
+// further ahead but cost a register copy of the buffer per tile -- 15 MOVs of ~200 instructions in an issue-bound loop.  Measured at
+// 1024 x 30 s (A/B): refill on top, 2 buffers 5.72 TB/s; in place, 2 buffers 6.06-6.11; 3 buffers 5.93 (128 registers); 4 buffers 6.12-6.22.
+#ifndef NTM_ESR_REFILL_LATE
+#define NTM_ESR_REFILL_LATE 1
+#endif
+constexpr int ESR_PF = NTM_ESR_PF;       // tiles of global loads in flight per warp
 constexpr int ESR_RING = 2048;           // on-chip window of past samples: power of two, >= ESR_TAPS
 // DCPreESR: one warp per CTA -- every loop bound then derives from blockIdx and the compiler keeps the control flow on the
 // uniform datapath (with 4 warps per CTA it doubled the shuffles, wrapped them in WARPSYNC pairs and emitted 5x the IMADs).
@@ -155,14 +164,15 @@ __global__ void __launch_bounds__(32 * esr_warps(DCPRE)) esr_kernel(const float*
             const long long nb = nb0 + TILE * u;
             if (nb >= c1) break;                                  // (warp-uniform)
             const long long n = nb + SPL * lane;
-            float xe[SPL], xt[SPL], ue[SPL], ut[SPL];
+            float xe[SPL], xt_copy[NTM_ESR_REFILL_LATE ? 1 : SPL], ue[SPL], ut[SPL];
+            float (&xt)[SPL] = *reinterpret_cast<float (*)[SPL]>(NTM_ESR_REFILL_LATE ? &pft[u][0] : &xt_copy[0]);
 #pragma unroll
             for (int j = 0; j < SPL; ++j) {
-                xt[j] = pft[u][j];
+                if (!NTM_ESR_REFILL_LATE) xt[j] = pft[u][j];
                 xe[j] = pft[u][j] - pfo[u][j];
             }
             // refill this buffer with the tile ESR_PF ahead
-            if (nb + TILE * ESR_PF < c1) fetch(nb + TILE * ESR_PF, pft[u], pfo[u]);
+            if (!NTM_ESR_REFILL_LATE && nb + TILE * ESR_PF < c1) fetch(nb + TILE * ESR_PF, pft[u], pfo[u]);
             {
                 // samples n - 1999 .. n - 2000 + SPL = elements 1 .. SPL - 1 of the aligned ring vectors at n - 2000 and the
                 // first element of the next lane's (lane 31: one scalar read); read BEFORE this tile overwrites its slots
@@ -220,6 +230,7 @@ __global__ void __launch_bounds__(32 * esr_warps(DCPRE)) esr_kernel(const float*
             }
             se_tile = fma(D32, se_tile, (double)__shfl_sync(0xffffffffu, ae, 31));
             st_tile = fma(D32, st_tile, (double)__shfl_sync(0xffffffffu, at, 31));
+            if (NTM_ESR_REFILL_LATE && nb + TILE * ESR_PF < c1) fetch(nb + TILE * ESR_PF, pft[u], pfo[u]);
           }
         }
     }
